@@ -1,0 +1,3 @@
+// oracle/shim: forwarding header (test infrastructure only)
+#pragma once
+#include "tbb.h"
