@@ -1,0 +1,115 @@
+/* pqb200.h -- C ABI of libpqb200.so, the B200 (sm_100a) permanent engine behind piquassoboost's
+ * permanent calculators.
+ *
+ * This is the drop-in boundary: plain pointers and sizes only, no C++/torch/numpy types.  Every
+ * entry point names the reference interface it replaces (paths relative to the reference tree,
+ * piquassoboost/...).  The precedent for an accelerator C ABI in the reference is the FPGA ("DFE")
+ * back end: init / compute(batch count, caller-allocated output) / release, resolved with dlsym
+ * (sampling/source/GlynnPermanentCalculatorDFE.cpp:47-58,117-145).
+ *
+ * Conventions
+ *   - matrices are row-major complex128 given as interleaved (re,im) doubles; `stride` is the
+ *     distance between rows in complex elements (common/source/matrix_base.hpp:44-51);
+ *   - all inputs are borrowed for the duration of the call only, outputs are caller allocated;
+ *   - every function returns 0 on success; on failure a non-zero code, and pqb200_last_error()
+ *     returns a message for the calling thread.  The C++ shims turn that into `throw std::string`
+ *     (the reference's error convention, e.g. BBFGPermanentCalculatorRepeated.hpp:122-123);
+ *   - there is NO CPU fallback: without a usable CUDA device every compute call fails;
+ *   - calls are serialised internally (one mutex), so the library may be called from the TBB
+ *     workers of samplingHelperFunctions.cpp:137 -- but the batched entry points are the intended
+ *     replacement for that loop.
+ *   - `ndev`: number of GPUs to shard one call over (0 = all initialised devices).
+ */
+#ifndef PQB200_H
+#define PQB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PQB200_OK 0
+#define PQB200_ERR_CUDA 1      /* CUDA runtime / driver / NCCL failure */
+#define PQB200_ERR_ARG 2       /* invalid argument (shape, size limit, null pointer) */
+#define PQB200_ERR_MISMATCH 3  /* sum(row multiplicities) != sum(column multiplicities) */
+
+/* Library life cycle.  Replaces initialize_DFE / releive_DFE (GlynnPermanentCalculatorDFE.cpp:125-166).
+ * pqb200_init(ndev): bind the first `ndev` visible CUDA devices (0 = all); idempotent; compute calls
+ * initialise lazily with all devices if it was never called. */
+int pqb200_init(int ndev);
+void pqb200_shutdown(void);
+int pqb200_device_count(void);
+const char* pqb200_last_error(void);
+const char* pqb200_version(void);
+
+/* perm(A) for one matrix.  Replaces
+ *   BBFGPermanentCalculator::calculate(matrix&, use_extended, use_inf)   sampling/source/BBFGPermanentCalculator.cpp:89-126
+ *   GlynnPermanentCalculator<M,P>::calculate(matrix&)                    sampling/source/GlynnPermanentCalculator.hpp:47-57
+ *   GlynnPermanentCalculatorSimple<M,P>::calculate(matrix&)              sampling/source/GlynnPermanentCalculatorSimple.hpp:47-53
+ * Edge semantics of the reference are kept: rows==0 || cols==0 -> 1; rows >= cols+2 -> 0; otherwise
+ * 2^-(rows-1) * sum over the 2^(rows-1) delta vectors of prod over the `cols` column sums. */
+int pqb200_permanent(const double* a, size_t rows, size_t cols, size_t stride, int ndev,
+                     double out[2]);
+
+/* One shard of perm(A): the partial, UNSCALED double-double sum over Gray-code chunk range
+ * shard_index of shard_count, computed on CUDA device `device`.  This is what one rank of a
+ * one-process-per-GPU job calls; the 4 doubles per rank (re.hi re.lo im.hi im.lo) are then
+ * all-gathered (NCCL) and folded with pqb200_permanent_combine.  When d_out is non-NULL it must be a
+ * device pointer on `device`: the partial is left there (no host sync) so that the collective can
+ * be enqueued directly behind the kernel on `stream` (a cudaStream_t, NULL = the library's own). */
+int pqb200_permanent_shard(const double* a, size_t rows, size_t cols, size_t stride, int device,
+                           uint64_t shard_index, uint64_t shard_count, double out_dd[4],
+                           double* d_out, void* stream);
+/* Fold `count` partials (4 doubles each) in index order with double-double adds and apply the
+ * exact 2^-(rows-1) scaling (reference: BBFGPermanentCalculator.hpp:227-232). */
+int pqb200_permanent_combine(const double* partials_dd, size_t count, size_t rows, double out[2]);
+
+/* Many plain permanents in one call: count matrices, matrix k is rows[k] x cols[k] with stride
+ * strides[k].  Replaces the list-of-matrices branch of the Python wrapper
+ * (sampling/GlynnPermanentCalculator_Wrapper.hpp:204-293). */
+int pqb200_permanent_batch(const double* const* a, const size_t* rows, const size_t* cols,
+                           const size_t* strides, size_t count, int ndev, double* out /* 2*count */);
+
+/* Repeated-row/column permanent.  row_mult[rows] = output-state occupations, col_mult[cols] =
+ * input-state occupations (argument order of the reference, Appendix A.3 of SURVEY.md).  Replaces
+ *   BBFGPermanentCalculatorRepeated::calculate(matrix&, col_mult, row_mult, use_extended, use_inf)
+ *                                                sampling/source/BBFGPermanentCalculatorRepeated.cpp:74-141
+ *   GlynnPermanentCalculatorRepeated<M,P>::calculate(matrix&, input_state, output_state)
+ *                                                sampling/source/GlynnPermanentCalculatorRepeated.hpp:49-74
+ * Returns PQB200_ERR_MISMATCH when the photon numbers differ (the reference throws std::string,
+ * BBFGPermanentCalculatorRepeated.hpp:119-124). */
+int pqb200_permanent_repeated(const double* a, size_t rows, size_t cols, size_t stride,
+                              const int64_t* row_mult, const int64_t* col_mult, int ndev,
+                              double out[2]);
+
+/* `count` repeated permanents of the SAME matrix with different occupation vectors
+ * (row_mults: count x rows, col_mults: count x cols, row-major).  Replaces the list-of-states
+ * branch of ChinHuhPermanentCalculator_Wrapper.hpp:233-326 and
+ * BatchednPermanentCalculator::calculate (sampling/source/BatchedPermanentCalculator.cpp:109-296). */
+int pqb200_permanent_repeated_batch(const double* a, size_t rows, size_t cols, size_t stride,
+                                    const int64_t* row_mults, const int64_t* col_mults,
+                                    size_t count, int ndev, double* out /* 2*count */);
+
+/* One photon step of the Clifford-Clifford B sampler for S shots at once.  For shot s:
+ *   pmf[s][m'] ~ | sum_i input[s][i] * perm(U[sample[s] rows, (input[s]-e_i) cols]) * U[m'][i] |^2
+ * normalised to sum 1.  Replaces compute_pmf (sampling/simulation_strategies/source/
+ * samplingHelperFunctions.cpp:78-342) called once per shot. */
+int pqb200_pmf_layer(const double* u, size_t m, size_t stride, const int64_t* samples /* S x m */,
+                     const int64_t* inputs /* S x m */, size_t S, int ndev, double* pmf /* S x m */);
+
+/* Timing of the most recent compute call on this thread (CUDA events around the kernels on device
+ * 0 of the call): kernel milliseconds, Gray steps executed, kernels launched. */
+typedef struct pqb200_stats {
+    double kernel_ms;
+    double gray_steps;
+    uint64_t launches;
+    int ndev;
+} pqb200_stats;
+int pqb200_last_stats(pqb200_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PQB200_H */

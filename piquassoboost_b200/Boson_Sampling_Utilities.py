@@ -1,0 +1,247 @@
+"""Python mirror of the reference's permanent-calculator classes, backed by the CUDA engine.
+
+Same class names, constructor arguments, `calculate()` behaviour, `lib` integers and attribute
+names (`matrix`, `input_state`, `output_state`) as
+piquassoboost/sampling/Boson_Sampling_Utilities.py:30-335 and the CPython types it derives from
+(sampling/GlynnPermanentCalculator_Wrapper.hpp:34-44,132-378;
+sampling/ChinHuhPermanentCalculator_Wrapper.hpp:36-47,143-408), so that
+
+    from piquassoboost_b200.Boson_Sampling_Utilities import GlynnPermanent
+    GlynnPermanent(A).calculate()
+
+is a drop-in for the reference import.  Every supported `lib` id is routed to the one numeric mode
+of the engine (FP64 products, double-double accumulation): the ids keep
+their meaning only as far as "which reference calculator would have been used".
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import Pqb200Error
+
+# lib ids of GlynnPermanentCalculator_wrapper (GlynnPermanentCalculator_Wrapper.hpp:34-44)
+GlynnRep = 0  # GlynnPermanentCalculatorLongDouble
+GlynnInf = 1
+GlynnSingleDFE = 2
+GlynnDualDFE = 3
+GlynnSingleDFEF = 4
+GlynnDualDFEF = 5
+GlynnDouble = 6
+BBFGDouble = 7
+BBFGLongDouble = 8
+GlynnSimpleDouble = 10
+GlynnSimpleLongDouble = 11
+GlynnB200 = 12  # new id: explicit request for the CUDA engine
+
+# lib ids of ChinHuhPermanentCalculator_wrapper (ChinHuhPermanentCalculator_Wrapper.hpp:36-47)
+ChinHuh = 0
+GlynnRepLongDouble = 1
+GlynnRepSingleDFE = 2
+GlynnRepDualDFE = 3
+GlynnRepMultiSingleDFE = 4
+GlynnRepMultiDualDFE = 5
+GlynnRepDouble = 6
+BBFGRepDouble = 7
+BBFGRepLongDouble = 8
+GlynnRepInf = 9
+GlynnRepB200 = 12
+
+_PLAIN_LIBS = {GlynnRep, GlynnDouble, BBFGDouble, BBFGLongDouble, GlynnSimpleDouble,
+               GlynnSimpleLongDouble, GlynnB200}
+_REPEATED_LIBS = {ChinHuh, GlynnRepLongDouble, GlynnRepDouble, BBFGRepDouble, BBFGRepLongDouble,
+                  GlynnRepB200}
+
+#: number of GPUs one calculate() call is sharded over (0 = all devices the library sees)
+DEFAULT_NDEV = 0
+
+
+def _plain_permanent(matrix, ndev):
+    m = _lib.as_matrix(matrix)
+    out = np.zeros(2, dtype=np.float64)
+    _lib.check(_lib.load().pqb200_permanent(_lib.dptr(m), m.shape[0], m.shape[1],
+                                            m.strides[0] // 16 if m.shape[1] else 0, ndev,
+                                            _lib.dptr(out)))
+    return complex(out[0], out[1])
+
+
+def _repeated_permanent(matrix, input_state, output_state, ndev):
+    m = _lib.as_matrix(matrix)
+    cols = _lib.as_state(input_state)   # input state  <-> column multiplicities
+    rows = _lib.as_state(output_state)  # output state <-> row multiplicities
+    if len(cols) != m.shape[1] or len(rows) != m.shape[0]:
+        raise Pqb200Error("state lengths do not match the matrix shape")
+    out = np.zeros(2, dtype=np.float64)
+    _lib.check(_lib.load().pqb200_permanent_repeated(
+        _lib.dptr(m), m.shape[0], m.shape[1], m.strides[0] // 16 if m.shape[1] else 0,
+        _lib.iptr(rows), _lib.iptr(cols), ndev, _lib.dptr(out)))
+    return complex(out[0], out[1])
+
+
+class GlynnPermanentCalculator_wrapper:
+    """Mirror of the CPython type of the same name: `(matrix, lib)`; `matrix` may be a list of
+    arrays, then `calculate()` returns a list (GlynnPermanentCalculator_Wrapper.hpp:204-293)."""
+
+    def __init__(self, matrix=None, lib=BBFGDouble, ndev=None):
+        self.lib = int(lib)
+        self.ndev = DEFAULT_NDEV if ndev is None else int(ndev)
+        self.matrix = matrix
+
+    @property
+    def matrix(self):
+        return self._matrix
+
+    @matrix.setter
+    def matrix(self, value):
+        if isinstance(value, (list, tuple)):
+            self._matrix = [_lib.as_matrix(v) for v in value]
+        elif value is None:
+            self._matrix = None
+        else:
+            self._matrix = _lib.as_matrix(value)
+
+    def calculate(self):
+        if self.lib not in _PLAIN_LIBS:
+            if self.lib in (GlynnSingleDFE, GlynnDualDFE, GlynnSingleDFEF, GlynnDualDFEF):
+                raise Pqb200Error("DFE (FPGA) permanent calculators are not part of this build")
+            if self.lib == GlynnInf:
+                raise Pqb200Error("MPFR Not included")  # BBFGPermanentCalculator.cpp:100-107
+            raise Pqb200Error("Wrong value set for permanent library.")
+        if self._matrix is None:
+            raise Pqb200Error("matrix is not set")
+        if isinstance(self._matrix, list):
+            return self._calculate_list(self._matrix)
+        return _plain_permanent(self._matrix, self.ndev)
+
+    def _calculate_list(self, mats):
+        lib = _lib.load()
+        n = len(mats)
+        if n == 0:
+            return []
+        ptrs = (_lib.c_double_p * n)(*[_lib.dptr(m) for m in mats])
+        rows = (ctypes.c_size_t * n)(*[m.shape[0] for m in mats])
+        cols = (ctypes.c_size_t * n)(*[m.shape[1] for m in mats])
+        strides = (ctypes.c_size_t * n)(*[m.strides[0] // 16 if m.shape[1] else 0 for m in mats])
+        out = np.zeros(2 * n, dtype=np.float64)
+        _lib.check(lib.pqb200_permanent_batch(ptrs, rows, cols, strides, n, self.ndev,
+                                              _lib.dptr(out)))
+        return [complex(out[2 * k], out[2 * k + 1]) for k in range(n)]
+
+
+class ChinHuhPermanentCalculator_wrapper:
+    """Mirror of the CPython type of the same name: `(lib, matrix, input_state, output_state)`.
+    States may be lists of arrays: the result is then a nested list [input][output]
+    (ChinHuhPermanentCalculator_Wrapper.hpp:233-326)."""
+
+    def __init__(self, lib=BBFGRepDouble, matrix=None, input_state=None, output_state=None,
+                 ndev=None):
+        self.lib = int(lib)
+        self.ndev = DEFAULT_NDEV if ndev is None else int(ndev)
+        self.matrix = None if matrix is None else _lib.as_matrix(matrix)
+        self.input_state = self._norm_state(input_state)
+        self.output_state = self._norm_state(output_state)
+
+    @staticmethod
+    def _norm_state(state):
+        if state is None:
+            return None
+        if isinstance(state, list) and len(state) and isinstance(state[0], np.ndarray):
+            return [_lib.as_state(s) for s in state]
+        return _lib.as_state(state)
+
+    def calculate(self):
+        if self.lib not in _REPEATED_LIBS:
+            if self.lib in (GlynnRepSingleDFE, GlynnRepDualDFE, GlynnRepMultiSingleDFE,
+                            GlynnRepMultiDualDFE, 10, 11):
+                raise Pqb200Error("DFE (FPGA) permanent calculators are not part of this build")
+            if self.lib == GlynnRepInf:
+                raise Pqb200Error("MPFR Not included")
+            raise Pqb200Error("Wrong value set for permanent library.")
+        ins, outs = self.input_state, self.output_state
+        if isinstance(ins, list) or isinstance(outs, list):
+            ins = ins if isinstance(ins, list) else [ins]
+            outs = outs if isinstance(outs, list) else [outs]
+            return self._calculate_lists(ins, outs)
+        return _repeated_permanent(self.matrix, ins, outs, self.ndev)
+
+    def _calculate_lists(self, ins, outs):
+        m = self.matrix
+        count = len(ins) * len(outs)
+        if count == 0:
+            return [[] for _ in ins]
+        rows = np.ascontiguousarray(np.stack([o for _ in ins for o in outs]), dtype=np.int64)
+        cols = np.ascontiguousarray(np.stack([i for i in ins for _ in outs]), dtype=np.int64)
+        out = np.zeros(2 * count, dtype=np.float64)
+        _lib.check(_lib.load().pqb200_permanent_repeated_batch(
+            _lib.dptr(m), m.shape[0], m.shape[1], m.strides[0] // 16, _lib.iptr(rows),
+            _lib.iptr(cols), count, self.ndev, _lib.dptr(out)))
+        vals = [complex(out[2 * k], out[2 * k + 1]) for k in range(count)]
+        return [vals[i * len(outs):(i + 1) * len(outs)] for i in range(len(ins))]
+
+
+class RepeatedPermanentCalculator(ChinHuhPermanentCalculator_wrapper):
+    """Boson_Sampling_Utilities.py:30-91."""
+
+    def __init__(self, lib, matrix, input_state, output_state):
+        if not isinstance(input_state, np.ndarray):
+            if not isinstance(input_state, list):
+                input_state = np.array(input_state, dtype=np.int64)
+            elif any(not isinstance(item, np.ndarray) for item in input_state):
+                if all(np.isscalar(item) for item in input_state):
+                    input_state = np.array(input_state, dtype=np.int64)
+                else:
+                    raise Exception('The input state should be a numpy array, or a list of numpy arrays')
+        if not isinstance(output_state, np.ndarray):
+            if not isinstance(output_state, list):
+                output_state = np.array(output_state, dtype=np.int64)
+            elif any(not isinstance(item, np.ndarray) for item in output_state):
+                if all(np.isscalar(item) for item in output_state):
+                    output_state = np.array(output_state, dtype=np.int64)
+                else:
+                    raise Exception('The output state should be a numpy array, or a list of numpy arrays')
+        super().__init__(lib=lib, matrix=matrix, input_state=input_state, output_state=output_state)
+
+
+def _repeated_class(name, lib, doc):
+    def __init__(self, matrix, input_state, output_state):
+        RepeatedPermanentCalculator.__init__(self, lib, matrix, input_state, output_state)
+    return type(name, (RepeatedPermanentCalculator,), {"__init__": __init__, "__doc__": doc})
+
+
+ChinHuhPermanentCalculator = _repeated_class(
+    "ChinHuhPermanentCalculator", ChinHuh, "Boson_Sampling_Utilities.py:96-99 (lib 0)")
+GlynnRepeatedPermanentCalculator = _repeated_class(
+    "GlynnRepeatedPermanentCalculator", GlynnRepLongDouble, "Boson_Sampling_Utilities.py:105-116 (lib 1)")
+GlynnRepeatedPermanentCalculatorDouble = _repeated_class(
+    "GlynnRepeatedPermanentCalculatorDouble", GlynnRepDouble, "Boson_Sampling_Utilities.py:167-177 (lib 6)")
+BBFGRepeatedPermanentCalculatorDouble = _repeated_class(
+    "BBFGRepeatedPermanentCalculatorDouble", BBFGRepDouble, "Boson_Sampling_Utilities.py:180-189 (lib 7)")
+BBFGRepeatedPermanentCalculatorLongDouble = _repeated_class(
+    "BBFGRepeatedPermanentCalculatorLongDouble", BBFGRepLongDouble, "Boson_Sampling_Utilities.py:193-203 (lib 8)")
+GlynnRepeatedInfPermanentCalculator = _repeated_class(
+    "GlynnRepeatedInfPermanentCalculator", GlynnRepInf, "Boson_Sampling_Utilities.py:120-123 (lib 9; raises: no MPFR)")
+
+
+def _plain_class(name, lib, doc):
+    def __init__(self, matrix):
+        GlynnPermanentCalculator_wrapper.__init__(self, matrix=matrix, lib=lib)
+    return type(name, (GlynnPermanentCalculator_wrapper,), {"__init__": __init__, "__doc__": doc})
+
+
+GlynnPermanent = _plain_class("GlynnPermanent", GlynnRep, "Boson_Sampling_Utilities.py:206-216 (lib 0)")
+GlynnPermanentInf = _plain_class("GlynnPermanentInf", GlynnInf, "Boson_Sampling_Utilities.py:218-228 (lib 1; raises: no MPFR)")
+GlynnPermanentDouble = _plain_class("GlynnPermanentDouble", GlynnDouble, "Boson_Sampling_Utilities.py:265-275 (lib 6)")
+BBFGPermanentDouble = _plain_class("BBFGPermanentDouble", BBFGDouble, "Boson_Sampling_Utilities.py:282-292 (lib 7)")
+BBFGPermanentLongDouble = _plain_class("BBFGPermanentLongDouble", BBFGLongDouble, "Boson_Sampling_Utilities.py:296-307 (lib 8)")
+GlynnPermanentSimpleDouble = _plain_class("GlynnPermanentSimpleDouble", GlynnSimpleDouble, "Boson_Sampling_Utilities.py:310-320 (lib 10)")
+GlynnPermanentSimpleLongDouble = _plain_class("GlynnPermanentSimpleLongDouble", GlynnSimpleLongDouble, "Boson_Sampling_Utilities.py:324-334 (lib 11)")
+
+
+def permanent_CPU_repeated_double(matrix, input_state, output_state):
+    """Name kept from sampling/permanent_calculators_wrapper.cpp:84-87 (runs on the GPU here)."""
+    return _repeated_permanent(matrix, input_state, output_state, DEFAULT_NDEV)
+
+
+def permanent_CPU_repeated_long_double(matrix, input_state, output_state):
+    """sampling/permanent_calculators_wrapper.cpp:157-160."""
+    return _repeated_permanent(matrix, input_state, output_state, DEFAULT_NDEV)

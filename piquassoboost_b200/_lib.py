@@ -1,0 +1,135 @@
+"""ctypes binding of libpqb200.so (the C ABI in include/pqb200.h).
+
+This is the reference-side binding a maintainer would otherwise write in C++;
+here it plays the role of the CPython extension layer of the reference
+(piquassoboost/sampling/GlynnPermanentCalculator_Wrapper.hpp, ChinHuhPermanentCalculator_Wrapper.hpp).
+There is no fallback: if the shared library is missing or CUDA is unusable, calls raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libpqb200.so")
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int64_p = ctypes.POINTER(ctypes.c_int64)
+c_size_p = ctypes.POINTER(ctypes.c_size_t)
+
+
+class Pqb200Stats(ctypes.Structure):
+    _fields_ = [
+        ("kernel_ms", ctypes.c_double),
+        ("gray_steps", ctypes.c_double),
+        ("launches", ctypes.c_uint64),
+        ("ndev", ctypes.c_int),
+    ]
+
+
+class Pqb200Error(Exception):
+    """Raised for every non-zero return code of the C ABI (the reference raises plain Exception
+    from `catch (std::string)`; this subclasses it so `except Exception` call sites keep working)."""
+
+
+_SIGNATURES = {
+    "pqb200_init": (ctypes.c_int, [ctypes.c_int]),
+    "pqb200_shutdown": (None, []),
+    "pqb200_device_count": (ctypes.c_int, []),
+    "pqb200_last_error": (ctypes.c_char_p, []),
+    "pqb200_version": (ctypes.c_char_p, []),
+    "pqb200_permanent": (
+        ctypes.c_int,
+        [c_double_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, c_double_p],
+    ),
+    "pqb200_permanent_shard": (
+        ctypes.c_int,
+        [c_double_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
+         ctypes.c_uint64, ctypes.c_uint64, c_double_p, ctypes.c_void_p, ctypes.c_void_p],
+    ),
+    "pqb200_permanent_combine": (
+        ctypes.c_int, [c_double_p, ctypes.c_size_t, ctypes.c_size_t, c_double_p]),
+    "pqb200_permanent_batch": (
+        ctypes.c_int,
+        [ctypes.POINTER(c_double_p), c_size_p, c_size_p, c_size_p, ctypes.c_size_t, ctypes.c_int,
+         c_double_p],
+    ),
+    "pqb200_permanent_repeated": (
+        ctypes.c_int,
+        [c_double_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, c_int64_p, c_int64_p,
+         ctypes.c_int, c_double_p],
+    ),
+    "pqb200_permanent_repeated_batch": (
+        ctypes.c_int,
+        [c_double_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, c_int64_p, c_int64_p,
+         ctypes.c_size_t, ctypes.c_int, c_double_p],
+    ),
+    "pqb200_pmf_layer": (
+        ctypes.c_int,
+        [c_double_p, ctypes.c_size_t, ctypes.c_size_t, c_int64_p, c_int64_p, ctypes.c_size_t,
+         ctypes.c_int, c_double_p],
+    ),
+    "pqb200_last_stats": (ctypes.c_int, [ctypes.POINTER(Pqb200Stats)]),
+}
+
+_lib = None
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def exported_symbols():
+    """Names of every entry point include/pqb200.h declares."""
+    return sorted(_SIGNATURES)
+
+
+def load():
+    """Load libpqb200.so (built in-tree by __graft_entry__.build() / csrc/Makefile)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise Pqb200Error(
+                f"{_LIB_PATH} is missing: build it with `make -C piquassoboost_b200/csrc` "
+                "(there is no CPU fallback)")
+        lib = ctypes.CDLL(_LIB_PATH)
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().pqb200_last_error()
+        raise Pqb200Error(msg.decode() if msg else f"pqb200 error code {rc}")
+
+
+def as_matrix(matrix):
+    """complex128, C-contiguous 2-D -- what PyArray_FROM_OTF(..., NPY_COMPLEX128, NPY_ARRAY_IN_ARRAY)
+    does in the reference wrappers (GlynnPermanentCalculator_Wrapper.hpp:151-157)."""
+    m = np.ascontiguousarray(matrix, dtype=np.complex128)
+    if m.ndim != 2:
+        raise Pqb200Error("matrix must be 2-dimensional")
+    return m
+
+
+def as_state(state):
+    return np.ascontiguousarray(state, dtype=np.int64).reshape(-1)
+
+
+def dptr(arr):
+    return arr.ctypes.data_as(c_double_p)
+
+
+def iptr(arr):
+    return arr.ctypes.data_as(c_int64_p)
+
+
+def last_stats():
+    st = Pqb200Stats()
+    check(load().pqb200_last_stats(ctypes.byref(st)))
+    return {"kernel_ms": st.kernel_ms, "gray_steps": st.gray_steps, "launches": int(st.launches),
+            "ndev": st.ndev}

@@ -1,0 +1,74 @@
+// glynn_plain_inst.cu -- instantiates glynn_plain_kernel<N> for N in [PQB_NLO, PQB_NHI] and registers
+// the launchers.  Compiled several times with different ranges (see Makefile) so that the ~45
+// instantiations build in parallel.
+#include "glynn_plain.cuh"
+#include "launch.h"
+
+#ifndef PQB_NLO
+#error "define PQB_NLO and PQB_NHI"
+#endif
+
+namespace pqb200 {
+
+template <int N>
+static cudaError_t launch_plain_n(const PlainLaunchArgs& x) {
+    static_assert(sizeof(PlainParams<N>) <= 32764, "kernel parameter space exceeded");
+    PlainParams<N> p;
+    const int rows = (int)x.rows, cols = (int)x.cols;
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++) {
+            double2 v = make_double2(0.0, 0.0);
+            if (i < rows && j < cols) {
+                v.x = 2.0 * x.a[2 * (i * x.stride + j)];
+                v.y = 2.0 * x.a[2 * (i * x.stride + j) + 1];
+            } else if (i == 0 && j >= cols) {
+                v.x = 2.0;  // padding column: column sum is the constant 1 (row 0 has delta = +1)
+            }
+            p.A2[i][j] = v;
+        }
+    p.rows = rows;
+    p.L = x.L;
+    p.chunk_begin = x.chunk_begin;
+    p.chunk_end = x.chunk_end;
+    const unsigned long long per_iter = (unsigned long long)x.grid * kPlainThreads;
+    p.iters = (unsigned int)((x.chunk_end - x.chunk_begin + per_iter - 1) / per_iter);
+    p.partials = x.partials;
+    p.counter = x.counter;
+    p.out = x.out;
+    glynn_plain_kernel<N><<<x.grid, kPlainThreads, 0, x.stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <int N>
+static int occupancy_plain_n(void) {
+    int nb = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, glynn_plain_kernel<N>,
+                                                                  kPlainThreads, 0);
+    return e == cudaSuccess ? nb : -1;
+}
+
+template <int LO, int HI>
+struct FillPlain {
+    static void go(plain_launch_fn* launch, plain_occupancy_fn* occ) {
+        launch[LO] = &launch_plain_n<LO>;
+        occ[LO] = &occupancy_plain_n<LO>;
+        FillPlain<LO + 1, HI>::go(launch, occ);
+    }
+};
+template <int HI>
+struct FillPlain<HI, HI> {
+    static void go(plain_launch_fn* launch, plain_occupancy_fn* occ) {
+        launch[HI] = &launch_plain_n<HI>;
+        occ[HI] = &occupancy_plain_n<HI>;
+    }
+};
+
+}  // namespace pqb200
+
+#define PQB_CAT2(a, b) a##b
+#define PQB_CAT(a, b) PQB_CAT2(a, b)
+
+extern "C" void PQB_CAT(pqb200_plain_fill_, PQB_NLO)(pqb200::plain_launch_fn* launch,
+                                                     pqb200::plain_occupancy_fn* occ) {
+    pqb200::FillPlain<PQB_NLO, PQB_NHI>::go(launch, occ);
+}

@@ -1,0 +1,415 @@
+// pqb200_capi.cu -- host side of libpqb200.so: the C ABI declared in include/pqb200.h.
+//
+// Host logic only: argument checks and the reference's edge cases, work planning (chunk length,
+// grid, shard ranges), kernel launches on one stream per device, and the double-double combine of
+// per-device partials.  There is no CPU compute path: without a CUDA device every call fails.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pqb200.h"
+#include "dd.cuh"
+#include "launch.h"
+
+using namespace pqb200;
+
+// registered by the glynn_plain_inst.cu units (one per N range, see Makefile PLAIN_RANGES)
+#define PQB_DECL_FILL(lo) \
+    extern "C" void pqb200_plain_fill_##lo(plain_launch_fn*, plain_occupancy_fn*);
+PQB_DECL_FILL(2)
+PQB_DECL_FILL(17)
+PQB_DECL_FILL(25)
+PQB_DECL_FILL(31)
+PQB_DECL_FILL(36)
+PQB_DECL_FILL(40)
+PQB_DECL_FILL(43)
+
+namespace {
+
+constexpr int kMaxPlainN = 45;
+constexpr int kMaxChunkLog = 12;  // re-seed the running column sums at least every 2^12 updates
+constexpr int kMaxGridBlocks = 4096;
+
+struct DeviceCtx {
+    int dev = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    double* partials = nullptr;  // kMaxGridBlocks x 4
+    unsigned int* counter = nullptr;
+    double* d_out = nullptr;  // 4 doubles
+    double* h_out = nullptr;  // pinned, 4 doubles
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int occ[kPlainTableSize];
+};
+
+std::mutex g_mu;
+std::vector<DeviceCtx> g_devs;
+bool g_tables_ready = false;
+plain_launch_fn g_plain_launch[kPlainTableSize];
+plain_occupancy_fn g_plain_occ[kPlainTableSize];
+
+thread_local std::string g_err;
+thread_local pqb200_stats g_stats = {0.0, 0.0, 0, 0};
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(PQB200_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e__) + \
+                                             " in " #expr);                                   \
+    } while (0)
+
+void fill_tables() {
+    if (g_tables_ready) return;
+    memset(g_plain_launch, 0, sizeof(g_plain_launch));
+    memset(g_plain_occ, 0, sizeof(g_plain_occ));
+    pqb200_plain_fill_2(g_plain_launch, g_plain_occ);
+    pqb200_plain_fill_17(g_plain_launch, g_plain_occ);
+    pqb200_plain_fill_25(g_plain_launch, g_plain_occ);
+    pqb200_plain_fill_31(g_plain_launch, g_plain_occ);
+    pqb200_plain_fill_36(g_plain_launch, g_plain_occ);
+    pqb200_plain_fill_40(g_plain_launch, g_plain_occ);
+    pqb200_plain_fill_43(g_plain_launch, g_plain_occ);
+    g_tables_ready = true;
+}
+
+// caller holds g_mu
+int init_locked(int ndev) {
+    fill_tables();
+    int visible = 0;
+    cudaError_t e = cudaGetDeviceCount(&visible);
+    if (e != cudaSuccess || visible <= 0)
+        return fail(PQB200_ERR_CUDA,
+                    std::string("no usable CUDA device (libpqb200 has no CPU fallback): ") +
+                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (ndev <= 0 || ndev > visible) ndev = visible;
+    while ((int)g_devs.size() < ndev) {
+        DeviceCtx c;
+        c.dev = (int)g_devs.size();
+        CUDA_TRY(cudaSetDevice(c.dev));
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, c.dev));
+        if (prop.major < 10)
+            return fail(PQB200_ERR_CUDA, std::string("device ") + prop.name +
+                                             " is not sm_100 class; this library is built for B200 only");
+        c.sm_count = prop.multiProcessorCount;
+        CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaMalloc(&c.partials, sizeof(double) * 4 * kMaxGridBlocks));
+        CUDA_TRY(cudaMalloc(&c.counter, sizeof(unsigned int)));
+        CUDA_TRY(cudaMemset(c.counter, 0, sizeof(unsigned int)));
+        CUDA_TRY(cudaMalloc(&c.d_out, sizeof(double) * 4));
+        CUDA_TRY(cudaMallocHost(&c.h_out, sizeof(double) * 4));
+        CUDA_TRY(cudaEventCreate(&c.e0));
+        CUDA_TRY(cudaEventCreate(&c.e1));
+        for (int i = 0; i < kPlainTableSize; i++) c.occ[i] = 0;
+        g_devs.push_back(c);
+    }
+    return PQB200_OK;
+}
+
+int ensure_devices(int ndev, int* used) {
+    if (g_devs.empty()) {
+        int rc = init_locked(0);
+        if (rc) return rc;
+    }
+    if (ndev <= 0 || ndev > (int)g_devs.size()) ndev = (int)g_devs.size();
+    *used = ndev;
+    return PQB200_OK;
+}
+
+struct PlainPlan {
+    int N;   // kernel template parameter (columns incl. padding)
+    int L;   // log2 chunk length
+    unsigned long long nchunks;
+};
+
+// Choose the chunk length: minimise  waves * (seed cost + 2^L * step cost)  for the busiest device.
+PlainPlan plan_plain(int rows, int cols, int max_resident_threads, unsigned long long shards) {
+    PlainPlan pl;
+    pl.N = std::max(rows, cols);
+    const int lmax = std::min(rows - 1, kMaxChunkLog);
+    double best = 1e300;
+    pl.L = lmax;
+    for (int L = 1; L <= lmax; L++) {
+        const unsigned long long C = 1ull << (rows - 1 - L);
+        const unsigned long long per_shard = (C + shards - 1) / shards;
+        const unsigned long long threads =
+            std::min<unsigned long long>((unsigned long long)max_resident_threads,
+                                         ((per_shard + kPlainThreads - 1) / kPlainThreads) * kPlainThreads);
+        const unsigned long long waves = (per_shard + threads - 1) / threads;
+        const double cost = (double)waves * (2.0 * rows * pl.N + (double)(1ull << L) * (6.0 * pl.N + 5.0));
+        if (cost < best * 0.999) {  // prefer the shorter chunk on ties (less rounding drift)
+            best = cost;
+            pl.L = L;
+        }
+    }
+    pl.nchunks = 1ull << (rows - 1 - pl.L);
+    return pl;
+}
+
+int plain_occupancy(DeviceCtx& c, int N) {
+    if (c.occ[N] == 0) {
+        cudaSetDevice(c.dev);
+        c.occ[N] = g_plain_occ[N]();
+    }
+    return c.occ[N];
+}
+
+// Launch the chunk range [cb, ce) of the plain kernel on device c (async on `stream`), result to `out`.
+int launch_plain_range(DeviceCtx& c, const double* a, size_t rows, size_t cols, size_t stride,
+                       const PlainPlan& pl, unsigned long long cb, unsigned long long ce,
+                       double* out, cudaStream_t stream) {
+    CUDA_TRY(cudaSetDevice(c.dev));
+    if (ce <= cb) {
+        CUDA_TRY(cudaMemsetAsync(out, 0, 4 * sizeof(double), stream));
+        return PQB200_OK;
+    }
+    const int occ = plain_occupancy(c, pl.N);
+    if (occ <= 0) return fail(PQB200_ERR_CUDA, "occupancy query failed for the plain kernel");
+    PlainLaunchArgs x;
+    x.a = a;
+    x.rows = rows;
+    x.cols = cols;
+    x.stride = stride;
+    x.L = pl.L;
+    x.chunk_begin = cb;
+    x.chunk_end = ce;
+    const unsigned long long want = (ce - cb + kPlainThreads - 1) / kPlainThreads;
+    x.grid = (int)std::min<unsigned long long>(want, (unsigned long long)std::min(kMaxGridBlocks, occ * c.sm_count));
+    x.partials = c.partials;
+    x.counter = c.counter;
+    x.out = out;
+    x.stream = stream;
+    CUDA_TRY(g_plain_launch[pl.N](x));
+    return PQB200_OK;
+}
+
+int check_plain_args(const double* a, size_t rows, size_t cols, size_t stride) {
+    if (!a) return fail(PQB200_ERR_ARG, "matrix pointer is null");
+    if (stride < cols) return fail(PQB200_ERR_ARG, "stride is smaller than the number of columns");
+    if (std::max(rows, cols) > (size_t)kMaxPlainN)
+        return fail(PQB200_ERR_ARG, "matrix dimension exceeds 45 (kernel-parameter resident matrix limit of this build)");
+    return PQB200_OK;
+}
+
+// reference edge cases (BBFGPermanentCalculator.hpp:90-95); returns true when `out` is final
+bool plain_edge_case(const double* a, size_t rows, size_t cols, size_t stride, double out[2]) {
+    if (rows == 0 || cols == 0) {
+        out[0] = 1.0;
+        out[1] = 0.0;
+        return true;
+    }
+    if (rows >= cols + 2) {
+        out[0] = 0.0;
+        out[1] = 0.0;
+        return true;
+    }
+    if (rows == 1) {
+        // a single row has one delta vector: the "sum" is the product of the row's entries
+        double re = 1.0, im = 0.0;
+        for (size_t j = 0; j < cols; j++) {
+            const double xr = a[2 * j], xi = a[2 * j + 1];
+            const double r = re * xr - im * xi, i = re * xi + im * xr;
+            re = r;
+            im = i;
+        }
+        (void)stride;
+        out[0] = re;
+        out[1] = im;
+        return true;
+    }
+    return false;
+}
+
+void combine_partials(const double* parts, size_t count, size_t rows, double out[2]) {
+    cdd tot = cdd_zero();
+    for (size_t k = 0; k < count; k++) {
+        cdd x;
+        x.re.hi = parts[4 * k + 0];
+        x.re.lo = parts[4 * k + 1];
+        x.im.hi = parts[4 * k + 2];
+        x.im.lo = parts[4 * k + 3];
+        cdd_add(tot, x);
+    }
+    const int e = -(int)(rows - 1);
+    out[0] = ldexp(tot.re.hi, e) + ldexp(tot.re.lo, e);
+    out[1] = ldexp(tot.im.hi, e) + ldexp(tot.im.lo, e);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pqb200_last_error(void) { return g_err.c_str(); }
+const char* pqb200_version(void) { return "pqb200 0.1 (sm_100a)"; }
+
+int pqb200_init(int ndev) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return init_locked(ndev);
+}
+
+void pqb200_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& c : g_devs) {
+        cudaSetDevice(c.dev);
+        cudaStreamSynchronize(c.stream);
+        cudaFree(c.partials);
+        cudaFree(c.counter);
+        cudaFree(c.d_out);
+        cudaFreeHost(c.h_out);
+        cudaEventDestroy(c.e0);
+        cudaEventDestroy(c.e1);
+        cudaStreamDestroy(c.stream);
+    }
+    g_devs.clear();
+}
+
+int pqb200_device_count(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_devs.empty()) {
+        if (init_locked(0)) return 0;
+    }
+    return (int)g_devs.size();
+}
+
+int pqb200_last_stats(pqb200_stats* out) {
+    if (!out) return fail(PQB200_ERR_ARG, "stats pointer is null");
+    *out = g_stats;
+    return PQB200_OK;
+}
+
+int pqb200_permanent(const double* a, size_t rows, size_t cols, size_t stride, int ndev,
+                     double out[2]) {
+    if (!out) return fail(PQB200_ERR_ARG, "output pointer is null");
+    if (rows != 0 && cols != 0) {
+        int rc = check_plain_args(a, rows, cols, stride);
+        if (rc) return rc;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    int used = 0;
+    // the library must be usable (CUDA present) even for the trivial cases: no silent CPU path
+    int rc = ensure_devices(ndev, &used);
+    if (rc) return rc;
+    g_stats = {0.0, 0.0, 0, used};
+    if (plain_edge_case(a, rows, cols, stride, out)) return PQB200_OK;
+
+    const int max_threads = g_devs[0].sm_count * kPlainThreads;  // refined per N below
+    PlainPlan pl = plan_plain((int)rows, (int)cols, max_threads, (unsigned long long)used);
+    if ((unsigned long long)used > pl.nchunks) used = (int)pl.nchunks;
+    std::vector<double> parts(4 * (size_t)used);
+    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
+    CUDA_TRY(cudaEventRecord(g_devs[0].e0, g_devs[0].stream));
+    for (int d = 0; d < used; d++) {
+        DeviceCtx& c = g_devs[d];
+        const unsigned long long cb = pl.nchunks * (unsigned long long)d / (unsigned long long)used;
+        const unsigned long long ce = pl.nchunks * (unsigned long long)(d + 1) / (unsigned long long)used;
+        rc = launch_plain_range(c, a, rows, cols, stride, pl, cb, ce, c.d_out, c.stream);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c.h_out, c.d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        if (d == 0) CUDA_TRY(cudaEventRecord(c.e1, c.stream));
+    }
+    for (int d = 0; d < used; d++) {
+        DeviceCtx& c = g_devs[d];
+        CUDA_TRY(cudaSetDevice(c.dev));
+        CUDA_TRY(cudaStreamSynchronize(c.stream));
+        memcpy(&parts[4 * (size_t)d], c.h_out, 4 * sizeof(double));
+    }
+    float ms = 0.f;
+    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
+    CUDA_TRY(cudaEventElapsedTime(&ms, g_devs[0].e0, g_devs[0].e1));
+    g_stats.kernel_ms = ms;
+    g_stats.gray_steps = ldexp(1.0, (int)rows - 1);
+    g_stats.launches = (uint64_t)used;
+    g_stats.ndev = used;
+    combine_partials(parts.data(), (size_t)used, rows, out);
+    return PQB200_OK;
+}
+
+int pqb200_permanent_shard(const double* a, size_t rows, size_t cols, size_t stride, int device,
+                           uint64_t shard_index, uint64_t shard_count, double out_dd[4],
+                           double* d_out, void* stream) {
+    if (shard_count == 0 || shard_index >= shard_count)
+        return fail(PQB200_ERR_ARG, "shard_index must be < shard_count");
+    if (!out_dd && !d_out) return fail(PQB200_ERR_ARG, "both output pointers are null");
+    int rc = check_plain_args(a, rows, cols, stride);
+    if (rc) return rc;
+    if (rows < 2 || rows >= cols + 2)
+        return fail(PQB200_ERR_ARG, "sharded evaluation needs 2 <= rows <= cols+1 (edge cases are not sharded)");
+    std::lock_guard<std::mutex> lk(g_mu);
+    int used = 0;
+    rc = ensure_devices(0, &used);
+    if (rc) return rc;
+    if (device < 0 || device >= (int)g_devs.size()) return fail(PQB200_ERR_ARG, "device index out of range");
+    DeviceCtx& c = g_devs[device];
+    PlainPlan pl = plan_plain((int)rows, (int)cols, c.sm_count * kPlainThreads, shard_count);
+    const unsigned long long cb = (unsigned long long)((__uint128_t)pl.nchunks * shard_index / shard_count);
+    const unsigned long long ce = (unsigned long long)((__uint128_t)pl.nchunks * (shard_index + 1) / shard_count);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c.stream;
+    double* dst = d_out ? d_out : c.d_out;
+    CUDA_TRY(cudaSetDevice(c.dev));
+    CUDA_TRY(cudaEventRecord(c.e0, st));
+    rc = launch_plain_range(c, a, rows, cols, stride, pl, cb, ce, dst, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(c.e1, st));
+    g_stats = {0.0, ldexp(1.0, (int)rows - 1 - pl.L) > 0 ? (double)(ce - cb) * ldexp(1.0, pl.L) : 0.0, 1, 1};
+    if (out_dd) {
+        CUDA_TRY(cudaMemcpyAsync(c.h_out, dst, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        memcpy(out_dd, c.h_out, 4 * sizeof(double));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, c.e0, c.e1));
+        g_stats.kernel_ms = ms;
+    }
+    return PQB200_OK;
+}
+
+int pqb200_permanent_combine(const double* partials_dd, size_t count, size_t rows, double out[2]) {
+    if (!partials_dd || !out) return fail(PQB200_ERR_ARG, "null pointer");
+    if (rows == 0) return fail(PQB200_ERR_ARG, "rows must be >= 1");
+    combine_partials(partials_dd, count, rows, out);
+    return PQB200_OK;
+}
+
+int pqb200_permanent_batch(const double* const* a, const size_t* rows, const size_t* cols,
+                           const size_t* strides, size_t count, int ndev, double* out) {
+    if (!out || (count && (!a || !rows || !cols || !strides))) return fail(PQB200_ERR_ARG, "null pointer");
+    // first cut: one launch per matrix; the batched small-matrix kernel replaces this loop
+    for (size_t k = 0; k < count; k++) {
+        int rc = pqb200_permanent(a[k], rows[k], cols[k], strides[k], ndev, out + 2 * k);
+        if (rc) return rc;
+    }
+    return PQB200_OK;
+}
+
+int pqb200_permanent_repeated(const double* a, size_t rows, size_t cols, size_t stride,
+                              const int64_t* row_mult, const int64_t* col_mult, int ndev,
+                              double out[2]) {
+    (void)a; (void)rows; (void)cols; (void)stride; (void)row_mult; (void)col_mult; (void)ndev; (void)out;
+    return fail(PQB200_ERR_ARG, "pqb200_permanent_repeated: not built yet");
+}
+
+int pqb200_permanent_repeated_batch(const double* a, size_t rows, size_t cols, size_t stride,
+                                    const int64_t* row_mults, const int64_t* col_mults,
+                                    size_t count, int ndev, double* out) {
+    (void)a; (void)rows; (void)cols; (void)stride; (void)row_mults; (void)col_mults; (void)count; (void)ndev; (void)out;
+    return fail(PQB200_ERR_ARG, "pqb200_permanent_repeated_batch: not built yet");
+}
+
+int pqb200_pmf_layer(const double* u, size_t m, size_t stride, const int64_t* samples,
+                     const int64_t* inputs, size_t S, int ndev, double* pmf) {
+    (void)u; (void)m; (void)stride; (void)samples; (void)inputs; (void)S; (void)ndev; (void)pmf;
+    return fail(PQB200_ERR_ARG, "pqb200_pmf_layer: not built yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+"""GPU parity tests of the plain Glynn/BBFG permanent through the C ABI / Python mirror.
+
+Oracle: the reference's own BBFGPermanentCalculator in long double (oracle/_ref), as required by
+SURVEY.md section 8(c).  Tolerance: 1e-10 relative (BASELINE.json north_star); the tests assert a
+tighter 1e-11 so that regressions in the compensated accumulation are caught early.
+"""
+import numpy as np
+import pytest
+
+from conftest import haar_unitary, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-11
+
+
+@pytest.fixture(scope="module")
+def pqb():
+    import piquassoboost_b200 as p
+    p.load()
+    return p
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 6, 7, 8, 10, 12, 13, 16, 17, 20, 22])
+def test_haar_unitary_vs_reference_long_double(pqb, ref, n):
+    A = haar_unitary(n, n)
+    got = pqb.GlynnPermanent(A).calculate()
+    want = ref.bbfg(A, long_double=True)
+    assert relerr(got, want) < TOL, (n, got, want)
+
+
+@pytest.mark.parametrize("n", [24, 26])
+def test_haar_submatrix_vs_reference_long_double(pqb, ref, n):
+    A = np.ascontiguousarray(haar_unitary(2 * n, 2 * n)[:n, :n])
+    got = pqb.BBFGPermanentLongDouble(A).calculate()
+    want = ref.bbfg(A, long_double=True)
+    assert relerr(got, want) < TOL, (n, got, want)
+
+
+def test_all_plain_classes_agree(pqb, ref):
+    A = haar_unitary(9, 99)
+    want = ref.bbfg(A, True)
+    for cls in (pqb.GlynnPermanent, pqb.GlynnPermanentDouble, pqb.BBFGPermanentDouble,
+                pqb.BBFGPermanentLongDouble, pqb.GlynnPermanentSimpleDouble,
+                pqb.GlynnPermanentSimpleLongDouble):
+        assert relerr(cls(A).calculate(), want) < TOL
+
+
+def test_edge_cases_match_reference(pqb, ref):
+    # rows==0 or cols==0 -> 1 ; rows >= cols+2 -> 0 (BBFGPermanentCalculator.hpp:90-95)
+    assert pqb.GlynnPermanent(np.zeros((0, 0), dtype=complex)).calculate() == 1
+    assert pqb.GlynnPermanent(np.ones((4, 2), dtype=complex)).calculate() == 0
+    one = np.array([[4.2 - 1j]])
+    assert relerr(pqb.GlynnPermanent(one).calculate(), ref.bbfg(one)) < 1e-15
+    # non-square inputs the reference accepts (rows <= cols+1): product over columns, sum over rows
+    rng = np.random.default_rng(3)
+    for shape in [(3, 5), (5, 4), (1, 3), (6, 6)]:
+        A = rng.normal(size=shape) + 1j * rng.normal(size=shape)
+        assert relerr(pqb.GlynnPermanent(A).calculate(), ref.bbfg(A)) < TOL, shape
+
+
+def test_non_contiguous_and_strided_input(pqb, ref):
+    big = haar_unitary(12, 5)
+    view = big[2:9, 3:10]              # non-contiguous view: wrapper must normalise it
+    assert relerr(pqb.GlynnPermanent(view).calculate(), ref.bbfg(np.ascontiguousarray(view))) < TOL
+    # explicit stride through the C ABI
+    from piquassoboost_b200 import _lib
+    out = np.zeros(2)
+    sub = big[:7]                      # 7 x 12 contiguous; use the first 7 columns with stride 12
+    _lib.check(_lib.load().pqb200_permanent(_lib.dptr(sub), 7, 7, 12, 1, _lib.dptr(out)))
+    assert relerr(complex(out[0], out[1]), ref.bbfg(np.ascontiguousarray(sub[:, :7]))) < TOL
+
+
+def test_structured_known_answers(pqb):
+    import math
+    # all-ones: n! ; rank one u v^T: n! prod u_i v_i ; identity: 1
+    for n in (5, 11, 18):
+        ones = np.ones((n, n), dtype=complex)
+        assert relerr(pqb.GlynnPermanent(ones).calculate(), math.factorial(n)) < 1e-12
+        rng = np.random.default_rng(n)
+        u = rng.normal(size=n) + 1j * rng.normal(size=n)
+        v = rng.normal(size=n) + 1j * rng.normal(size=n)
+        want = math.factorial(n) * np.prod(u) * np.prod(v)
+        assert relerr(pqb.GlynnPermanent(np.outer(u, v)).calculate(), want) < 1e-11
+        assert abs(pqb.GlynnPermanent(np.eye(n)).calculate() - 1) < 1e-12
+
+
+def test_list_of_matrices(pqb, ref):
+    mats = [haar_unitary(n, 100 + n) for n in (3, 6, 4, 9)]
+    got = pqb.GlynnPermanentCalculator_wrapper(mats, 7).calculate()
+    assert isinstance(got, list) and len(got) == 4
+    for g, m in zip(got, mats):
+        assert relerr(g, ref.bbfg(m)) < TOL
+
+
+def test_shard_invariance_and_combine(pqb):
+    from piquassoboost_b200 import _lib
+    lib = _lib.load()
+    A = haar_unitary(21, 21)
+    whole = pqb.GlynnPermanent(A).calculate()
+    for shards in (1, 2, 3, 8):
+        parts = np.zeros(4 * shards)
+        for k in range(shards):
+            out = np.zeros(4)
+            _lib.check(lib.pqb200_permanent_shard(_lib.dptr(A), 21, 21, 21, 0, k, shards,
+                                                  _lib.dptr(out), None, None))
+            parts[4 * k:4 * k + 4] = out
+        res = np.zeros(2)
+        _lib.check(lib.pqb200_permanent_combine(_lib.dptr(parts), shards, 21, _lib.dptr(res)))
+        assert relerr(complex(res[0], res[1]), whole) < 1e-13
+
+
+def test_errors_are_raised_not_swallowed(pqb):
+    with pytest.raises(Exception):
+        pqb.GlynnPermanent(np.ones((46, 46), dtype=complex)).calculate()   # above the size limit
+    with pytest.raises(Exception):
+        pqb.GlynnPermanentCalculator_wrapper(np.eye(3), 3).calculate()    # DFE id
+    with pytest.raises(Exception):
+        pqb.GlynnPermanentInf(np.eye(3)).calculate()                      # MPFR id
