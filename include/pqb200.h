@@ -109,6 +109,11 @@ typedef struct pqb200_stats {
 } pqb200_stats;
 int pqb200_last_stats(pqb200_stats* out);
 
+/* Measurement aid (no reference counterpart): sustained issue rate of the FP64 pipe on `device`
+ * in thread-instructions per second, from independent chains of op 0 = DFMA, 1 = DADD, 2 = DMUL
+ * running for about duration_hint_s seconds.  bench.py uses it as the roofline denominator. */
+int pqb200_fp64_peak(int device, int op, double duration_hint_s, double* thread_instr_per_s);
+
 #ifdef __cplusplus
 }
 #endif

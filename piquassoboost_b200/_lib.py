@@ -70,6 +70,7 @@ _SIGNATURES = {
          ctypes.c_int, c_double_p],
     ),
     "pqb200_last_stats": (ctypes.c_int, [ctypes.POINTER(Pqb200Stats)]),
+    "pqb200_fp64_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_double, c_double_p]),
 }
 
 _lib = None

@@ -178,7 +178,7 @@ __device__ __forceinline__ void term_acc(const double (&cr)[N], const double (&c
     cmul_acc<NEG>(acc_re, acc_im, qr[0], qi[0], cr[N - 1], ci[N - 1]);
 }
 
-// c += sg * row   (sg = +-1 in a register; row in uniform registers)
+// c += sg * row   (sg = +-1 (or +-0.5 when seeding) in a register; row in uniform registers)
 template <int N>
 __device__ __forceinline__ void toggle_row(const PlainParams<N>& p, int row, double sg,
                                            double (&cr)[N], double (&ci)[N]) {
@@ -216,26 +216,28 @@ glynn_plain_kernel(const __grid_constant__ PlainParams<N> p) {
             toggle_row<N>(p, i, d, cr, ci);
         }
         cdd cacc = cdd_zero();
+        const unsigned int g0lo = (unsigned int)g0;
 #pragma unroll 1
         for (unsigned int s = 0; s < nsteps; s += 2) {
-            // two consecutive terms s, s+1 (s even): Gray bit 0 is set at s+1 iff bit 1 of s is clear
+            // two consecutive terms g, g+1 (g = g0+s even): Gray bit 0 is set going into g+1 iff bit 1
+            // of g is clear (warp-uniform whenever L >= 2)
             double bs_re = 0.0, bs_im = 0.0;
             term_acc<N, false>(cr, ci, bs_re, bs_im);
-            toggle_row<N>(p, rows - 1, ((s >> 1) & 1u) ? 1.0 : -1.0, cr, ci);
+            toggle_row<N>(p, rows - 1, (((g0lo | s) >> 1) & 1u) ? 1.0 : -1.0, cr, ci);
             term_acc<N, true>(cr, ci, bs_re, bs_im);
             dd_add_d(cacc.re, bs_re);
             dd_add_d(cacc.im, bs_im);
-            // ---- general toggle into term s+2: Gray bit b = ctz(s+2) >= 1, warp-uniform row,
-            //      per-thread sign (it depends on the chunk index only for b == L-1)
+            // ---- general toggle into term g+2: Gray bit b = ctz(s+2) >= 1, warp-uniform row, per-thread
+            // sign (it depends on the chunk index only for b == L-1).  Unconditional so that the loop
+            // body is one basic block: after the last pair b == L and row rows-1-L >= 0 is toggled
+            // into column sums that are never used again.
             const unsigned int s2 = s + 2;
-            if (s2 < nsteps) {
-                const int b = __ffs(s2) - 1;
-                const unsigned long long g = g0 + s2;
-                const double sg = (((g >> b) ^ (g >> (b + 1))) & 1ull) ? -1.0 : 1.0;
-                toggle_row<N>(p, rows - 1 - b, sg, cr, ci);
-            }
+            const int b = __ffs(s2) - 1;
+            const unsigned long long g = g0 + s2;
+            const double sg = (((g >> b) ^ (g >> (b + 1))) & 1ull) ? -1.0 : 1.0;
+            toggle_row<N>(p, rows - 1 - b, sg, cr, ci);
         }
-        // every 2-term block starts with the parity of the chunk's start code
+        // every group of terms starts with the parity of the chunk's start code
         if (__popcll(gray0) & 1) {
             cacc.re = dd_neg(cacc.re);
             cacc.im = dd_neg(cacc.im);

@@ -84,22 +84,29 @@ void fill_tables() {
     g_tables_ready = true;
 }
 
-// caller holds g_mu
-int init_locked(int ndev) {
+int g_visible = -1;      // CUDA devices visible to this process
+int g_default_ndev = 0;  // devices one call is sharded over when the caller passes ndev == 0
+
+// caller holds g_mu.  Creates the per-device context (stream, workspaces) on first use only, so
+// that a one-process-per-GPU job touches nothing but its own device.
+int get_device(int dev, DeviceCtx** out) {
     fill_tables();
-    int visible = 0;
-    cudaError_t e = cudaGetDeviceCount(&visible);
-    if (e != cudaSuccess || visible <= 0)
-        return fail(PQB200_ERR_CUDA,
-                    std::string("no usable CUDA device (libpqb200 has no CPU fallback): ") +
-                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
-    if (ndev <= 0 || ndev > visible) ndev = visible;
-    while ((int)g_devs.size() < ndev) {
-        DeviceCtx c;
-        c.dev = (int)g_devs.size();
-        CUDA_TRY(cudaSetDevice(c.dev));
+    if (g_visible < 0) {
+        int visible = 0;
+        cudaError_t e = cudaGetDeviceCount(&visible);
+        if (e != cudaSuccess || visible <= 0)
+            return fail(PQB200_ERR_CUDA,
+                        std::string("no usable CUDA device (libpqb200 has no CPU fallback): ") +
+                            (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+        g_visible = visible;
+        g_devs.resize((size_t)visible);
+    }
+    if (dev < 0 || dev >= g_visible) return fail(PQB200_ERR_ARG, "device index out of range");
+    DeviceCtx& c = g_devs[(size_t)dev];
+    if (c.dev < 0) {
+        CUDA_TRY(cudaSetDevice(dev));
         cudaDeviceProp prop;
-        CUDA_TRY(cudaGetDeviceProperties(&prop, c.dev));
+        CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
         if (prop.major < 10)
             return fail(PQB200_ERR_CUDA, std::string("device ") + prop.name +
                                              " is not sm_100 class; this library is built for B200 only");
@@ -113,17 +120,33 @@ int init_locked(int ndev) {
         CUDA_TRY(cudaEventCreate(&c.e0));
         CUDA_TRY(cudaEventCreate(&c.e1));
         for (int i = 0; i < kPlainTableSize; i++) c.occ[i] = 0;
-        g_devs.push_back(c);
+        c.dev = dev;
     }
+    if (out) *out = &c;
     return PQB200_OK;
 }
 
+// caller holds g_mu
+int init_locked(int ndev) {
+    int rc = get_device(0, nullptr);
+    if (rc) return rc;
+    if (ndev <= 0 || ndev > g_visible) ndev = g_visible;
+    g_default_ndev = ndev;
+    return PQB200_OK;
+}
+
+// resolves the `ndev` argument of a compute call and makes sure those devices have contexts
 int ensure_devices(int ndev, int* used) {
-    if (g_devs.empty()) {
+    if (g_default_ndev == 0) {
         int rc = init_locked(0);
         if (rc) return rc;
     }
-    if (ndev <= 0 || ndev > (int)g_devs.size()) ndev = (int)g_devs.size();
+    if (ndev <= 0) ndev = g_default_ndev;
+    if (ndev > g_visible) ndev = g_visible;
+    for (int d = 0; d < ndev; d++) {
+        int rc = get_device(d, nullptr);
+        if (rc) return rc;
+    }
     *used = ndev;
     return PQB200_OK;
 }
@@ -262,6 +285,7 @@ int pqb200_init(int ndev) {
 void pqb200_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto& c : g_devs) {
+        if (c.dev < 0) continue;
         cudaSetDevice(c.dev);
         cudaStreamSynchronize(c.stream);
         cudaFree(c.partials);
@@ -273,14 +297,16 @@ void pqb200_shutdown(void) {
         cudaStreamDestroy(c.stream);
     }
     g_devs.clear();
+    g_visible = -1;
+    g_default_ndev = 0;
 }
 
 int pqb200_device_count(void) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_devs.empty()) {
+    if (g_default_ndev == 0) {
         if (init_locked(0)) return 0;
     }
-    return (int)g_devs.size();
+    return g_default_ndev;
 }
 
 int pqb200_last_stats(pqb200_stats* out) {
@@ -347,11 +373,10 @@ int pqb200_permanent_shard(const double* a, size_t rows, size_t cols, size_t str
     if (rows < 2 || rows >= cols + 2)
         return fail(PQB200_ERR_ARG, "sharded evaluation needs 2 <= rows <= cols+1 (edge cases are not sharded)");
     std::lock_guard<std::mutex> lk(g_mu);
-    int used = 0;
-    rc = ensure_devices(0, &used);
+    DeviceCtx* cp = nullptr;
+    rc = get_device(device, &cp);
     if (rc) return rc;
-    if (device < 0 || device >= (int)g_devs.size()) return fail(PQB200_ERR_ARG, "device index out of range");
-    DeviceCtx& c = g_devs[device];
+    DeviceCtx& c = *cp;
     PlainPlan pl = plan_plain((int)rows, (int)cols, c.sm_count * kPlainThreads, shard_count);
     const unsigned long long cb = (unsigned long long)((__uint128_t)pl.nchunks * shard_index / shard_count);
     const unsigned long long ce = (unsigned long long)((__uint128_t)pl.nchunks * (shard_index + 1) / shard_count);

@@ -15,7 +15,7 @@ lib = _lib.load()
 out = np.zeros(4)
 for r in range(reps):
     t = time.time()
-    _lib.check(lib.pqb200_permanent_shard(_lib.dptr(A), n, n, n, 0, 1, shards, _lib.dptr(out), None, None))
+    _lib.check(lib.pqb200_permanent_shard(_lib.dptr(A), n, n, n, 0, shards // 2, shards, _lib.dptr(out), None, None))
     st = _lib.last_stats()
     print(f"n={n} shard 1/{shards}: kernel {st['kernel_ms']:.3f} ms, {st['gray_steps']/st['kernel_ms']*1e3:.4e} steps/s, "
           f"{st['gray_steps']*8*n/st['kernel_ms']/1e9:.2f} TFLOP/s, wall {1e3*(time.time()-t):.1f} ms", out)
