@@ -161,7 +161,10 @@ def run_b200(args, rank, local_rank, world):
     a_ptr = ctypes.cast(A_host.data_ptr(), _lib.c_double_p)
     partial = torch.zeros(4, dtype=torch.float64, device=dev)
     gathered = torch.zeros(4 * world, dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: its handle is passed to the C ABI so that the kernel, the NCCL
+    # all-gather and the timing events are all ordered on the same stream
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
 
     def step():
         _lib.check(lib.pqb200_permanent_shard(a_ptr, n, n, n, local_rank, rank, world, None,

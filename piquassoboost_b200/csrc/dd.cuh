@@ -50,6 +50,16 @@ __host__ __device__ __forceinline__ void dd_add_dd(dd& acc, const dd& x) {
     acc.hi = hi2;
 }
 
+// x * f with f a plain double, error-free product of the leading parts (FMA two-prod)
+__host__ __device__ __forceinline__ dd dd_mul_d(const dd& x, double f) {
+    const double p = x.hi * f;
+    const double e = fma(x.hi, f, -p) + x.lo * f;
+    dd r;
+    r.hi = p + e;
+    r.lo = e - (r.hi - p);
+    return r;
+}
+
 __host__ __device__ __forceinline__ dd dd_neg(const dd& x) {
     dd r;
     r.hi = -x.hi;

@@ -1,0 +1,175 @@
+// glynn_repeated.cuh -- repeated-row (n-ary Gray code) Glynn / BBFG permanent kernel for sm_100a.
+//
+// What it computes (reference: piquassoboost/sampling/source/BBFGPermanentCalculatorRepeated.hpp:116-307,
+// n-ary counter: common/source/n_aryGrayCodeCounter.cpp:114-240).  After the reference's anchor-row
+// step (hpp:78-94) the rows 1..D carry multiplicities r_i and
+//
+//   perm = 2^-(N-1) sum_{0<=k_i<=r_i} (-1)^{sum k} prod_i C(r_i,k_i) prod_j (a_0j + sum_i (r_i-2k_i) a_ij)
+//
+// where j runs over the PHYSICALLY REPEATED columns (the host expands column multiplicities, so
+// the product chain is the plain kernel's).  The k vectors are visited in the reference's reflected
+// mixed-radix Gray order: digit d (row d+1, radix r_d+1), digit 0 least significant.
+//
+// GPU layout.  The digit space is split into LOW digits 0..q-1 (swept inside a chunk, `len` =
+// prod of their radices steps) and HIGH digits q..D-1 (one combination per chunk; a thread owns a
+// chunk).  Three facts make the chunk loop as cheap as the plain kernel's:
+//   1. which low digit changes at local step t depends on t only -> the toggled ROW is
+//      warp-uniform and its data comes from the kernel-parameter constant bank (LDCU -> uniform
+//      register operands), exactly as in glynn_plain.cuh;
+//   2. the direction of the change depends on the thread only through one bit, the parity P of the
+//      thread's high Gray digits: a digit is either mirrored (k -> r-k) for all steps or not at all.
+//      The host tabulates both directions per step; the thread selects with P;
+//   3. C(r,k) = C(r,r-k), so the binomial weight of the low digits is the same for mirrored and
+//      unmirrored threads: it is tabulated per step, pre-multiplied with the alternating parity.
+// Per step: one 16-byte uniform table load, 2N DFMA (update), 4(N-1) DMUL/DFMA (product), 2 DFMA
+// (weighted accumulate).  Accumulation is double-double as in the plain kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dd.cuh"
+#include "glynn_plain.cuh"
+#include "launch.h"
+
+namespace pqb200 {
+
+constexpr int kRepMaxN = 44;      // 16*N*N + header must fit the kernel parameter space
+constexpr int kRepMaxDigits = 44;
+
+// one entry per local step t of a chunk (entry 0: only `w` is used)
+struct __align__(16) RepStep {
+    double w;            // (-1)^t * prod_{low digits} C(r_d, k_d(t))
+    int row;             // matrix row toggled going into step t (1..D)
+    unsigned int flags;  // bit P: 1 if k increases (column sums -= 2a) for a thread with high parity P
+};
+
+template <int N>
+struct RepParams {
+    double2 A2[N][N];  // 2*a, row 0 = anchor, rows 1..D = digit rows, columns physically repeated
+    int D;             // number of digits (rows - 1)
+    int q;             // number of low digits
+    unsigned int len;  // steps per chunk = prod_{d<q} radix[d]
+    unsigned long long chunk_begin, chunk_end;
+    unsigned int iters;
+    unsigned char radix[kRepMaxDigits];      // r_d + 1
+    unsigned long long weight[kRepMaxDigits];  // prod_{q<=l<d} radix[l]  (d >= q)
+    const RepStep* table;   // [len]
+    const double2* base;    // [2][N]: a_0 + sum_{low d} (+-r_d) a_d for P = 0 / 1   (NOT doubled)
+    const double* binom;    // [D][kRepMaxN+1]: C(r_d, k)
+    const int* low_parity;  // [2]: parity of sum of the low digits' initial k for P = 0 / 1
+    double* partials;
+    unsigned int* counter;
+    double* out;
+};
+
+// prod_j c[j]
+template <int N>
+__device__ __forceinline__ void term_prod(const double (&cr)[N], const double (&ci)[N], double& pr,
+                                          double& pi) {
+    constexpr int CH = (N >= 16) ? 4 : (N >= 4 ? 2 : 1);
+    double qr[CH], qi[CH];
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+        qr[k] = cr[k];
+        qi[k] = ci[k];
+    }
+#pragma unroll
+    for (int j = CH; j < N; j++) cmul(qr[j % CH], qi[j % CH], cr[j], ci[j]);
+    if (CH == 4) {
+        cmul(qr[0], qi[0], qr[1], qi[1]);
+        cmul(qr[2], qi[2], qr[3], qi[3]);
+        cmul(qr[0], qi[0], qr[2], qi[2]);
+    } else if (CH == 2) {
+        cmul(qr[0], qi[0], qr[1], qi[1]);
+    }
+    pr = qr[0];
+    pi = qi[0];
+}
+
+template <int N>
+__device__ __forceinline__ void rep_toggle(const RepParams<N>& p, int row, double sg,
+                                           double (&cr)[N], double (&ci)[N]) {
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        cr[j] = fma(sg, p.A2[row][j].x, cr[j]);
+        ci[j] = fma(sg, p.A2[row][j].y, ci[j]);
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(kPlainThreads, 1)
+glynn_repeated_kernel(const __grid_constant__ RepParams<N> p) {
+    const int D = p.D, q = p.q;
+    const unsigned int len = p.len;
+    const unsigned long long nthreads = (unsigned long long)gridDim.x * kPlainThreads;
+    cdd tot = cdd_zero();
+    unsigned long long c =
+        p.chunk_begin + (unsigned long long)blockIdx.x * kPlainThreads + threadIdx.x;
+    for (unsigned int it = 0; it < p.iters; it++, c += nthreads) {
+        const bool live = c < p.chunk_end;
+        const unsigned long long cc = live ? c : p.chunk_begin;
+        // ---- decode the high digits (most significant first), build their reflected Gray values,
+        //      the high part of the column sums, the binomial weight and the parity
+        //      (n_aryGrayCodeCounter::initialize, n_aryGrayCodeCounter.cpp:114-140)
+        int par = 0, ksum = 0;
+        double whigh = 1.0;
+        double hr[N], hi[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) hr[j] = hi[j] = 0.0;
+#pragma unroll 1
+        for (int d = D - 1; d >= q; d--) {
+            const int radix = p.radix[d];
+            const int cnt = (int)((cc / p.weight[d]) % (unsigned long long)radix);
+            const int k = par ? radix - 1 - cnt : cnt;
+            par ^= k & 1;
+            ksum += k;
+            whigh *= p.binom[d * (kRepMaxN + 1) + k];
+            rep_toggle<N>(p, d + 1, 0.5 * (double)(radix - 1 - 2 * k), hr, hi);
+        }
+        const int P = par;
+        double cr[N], ci[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            const double2 b = p.base[P * N + j];
+            cr[j] = b.x + hr[j];
+            ci[j] = b.y + hi[j];
+        }
+        // ---- sweep the low digits
+        cdd cacc = cdd_zero();
+        double bs_re = 0.0, bs_im = 0.0;
+        {
+            double pr, pi;
+            term_prod<N>(cr, ci, pr, pi);
+            const double w = p.table[0].w;
+            bs_re = w * pr;
+            bs_im = w * pi;
+        }
+#pragma unroll 1
+        for (unsigned int t = 1; t < len; t++) {
+            const RepStep e = p.table[t];
+            const double sg = ((e.flags >> P) & 1u) ? -1.0 : 1.0;
+            rep_toggle<N>(p, e.row, sg, cr, ci);
+            double pr, pi;
+            term_prod<N>(cr, ci, pr, pi);
+            bs_re = fma(e.w, pr, bs_re);
+            bs_im = fma(e.w, pi, bs_im);
+            if (t & 1u) {
+                dd_add_d(cacc.re, bs_re);
+                dd_add_d(cacc.im, bs_im);
+                bs_re = 0.0;
+                bs_im = 0.0;
+            }
+        }
+        dd_add_d(cacc.re, bs_re);
+        dd_add_d(cacc.im, bs_im);
+        // ---- thread-constant factors: high binomials and the parity of the chunk's first term
+        const double f = (((ksum + p.low_parity[P]) & 1) ? -whigh : whigh) * (live ? 1.0 : 0.0);
+        cdd scaled;  // f is an exactly representable integer (< 2^53 for N <= 53)
+        scaled.re = dd_mul_d(cacc.re, f);
+        scaled.im = dd_mul_d(cacc.im, f);
+        cdd_add(tot, scaled);
+    }
+    grid_reduce_cdd<kPlainThreads>(tot, p.partials, p.counter, p.out);
+}
+
+}  // namespace pqb200

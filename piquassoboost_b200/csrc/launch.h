@@ -23,6 +23,28 @@ struct PlainLaunchArgs {
 typedef cudaError_t (*plain_launch_fn)(const PlainLaunchArgs&);
 typedef int (*plain_occupancy_fn)(void);  // resident CTAs per SM on the current device (<=0: error)
 
+struct RepLaunchArgs {
+    const double* mat;  // host, interleaved complex, R x N (row 0 = anchor, columns physically repeated)
+    int R, N;
+    int q;
+    unsigned int len;
+    unsigned long long chunk_begin, chunk_end;
+    int grid;
+    const unsigned char* radix;        // [R-1]
+    const unsigned long long* weight;  // [R-1]
+    const void* table;                 // device, RepStep[len]
+    const void* base;                  // device, double2[2][N]
+    const double* binom;               // device, [R-1][kRepBinomStride]
+    const int* low_parity;             // device, [2]
+    double* partials;
+    unsigned int* counter;
+    double* out;
+    cudaStream_t stream;
+};
+
+typedef cudaError_t (*rep_launch_fn)(const RepLaunchArgs&);
+
+constexpr int kRepBinomStride = 45;  // kRepMaxN + 1
 constexpr int kPlainTableSize = 64;
 constexpr int kPlainThreads = 256;  // CTA size of glynn_plain_kernel
 

@@ -16,6 +16,7 @@
 #include "../../include/pqb200.h"
 #include "dd.cuh"
 #include "launch.h"
+#include "repeated_host.h"
 
 using namespace pqb200;
 
@@ -29,12 +30,22 @@ PQB_DECL_FILL(31)
 PQB_DECL_FILL(36)
 PQB_DECL_FILL(40)
 PQB_DECL_FILL(43)
+#define PQB_DECL_REP_FILL(lo) extern "C" void pqb200_rep_fill_##lo(rep_launch_fn*);
+PQB_DECL_REP_FILL(2)
+PQB_DECL_REP_FILL(17)
+PQB_DECL_REP_FILL(25)
+PQB_DECL_REP_FILL(31)
+PQB_DECL_REP_FILL(36)
+PQB_DECL_REP_FILL(40)
+PQB_DECL_REP_FILL(43)
 
 namespace {
 
 constexpr int kMaxPlainN = 45;
 constexpr int kMaxChunkLog = 12;  // re-seed the running column sums at least every 2^12 updates
 constexpr int kMaxGridBlocks = 4096;
+constexpr int kMaxRepN = 44;
+constexpr unsigned int kMaxRepLen = 4096;  // steps per chunk of the repeated kernel (table size)
 
 struct DeviceCtx {
     int dev = -1;
@@ -46,6 +57,11 @@ struct DeviceCtx {
     double* h_out = nullptr;  // pinned, 4 doubles
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int occ[kPlainTableSize];
+    // repeated-row kernel tables (device): step table, base vectors, binomials, low parities
+    void* rep_table = nullptr;
+    void* rep_base = nullptr;
+    double* rep_binom = nullptr;
+    int* rep_lowpar = nullptr;
 };
 
 std::mutex g_mu;
@@ -53,6 +69,7 @@ std::vector<DeviceCtx> g_devs;
 bool g_tables_ready = false;
 plain_launch_fn g_plain_launch[kPlainTableSize];
 plain_occupancy_fn g_plain_occ[kPlainTableSize];
+rep_launch_fn g_rep_launch[kPlainTableSize];
 
 thread_local std::string g_err;
 thread_local pqb200_stats g_stats = {0.0, 0.0, 0, 0};
@@ -81,6 +98,14 @@ void fill_tables() {
     pqb200_plain_fill_36(g_plain_launch, g_plain_occ);
     pqb200_plain_fill_40(g_plain_launch, g_plain_occ);
     pqb200_plain_fill_43(g_plain_launch, g_plain_occ);
+    memset(g_rep_launch, 0, sizeof(g_rep_launch));
+    pqb200_rep_fill_2(g_rep_launch);
+    pqb200_rep_fill_17(g_rep_launch);
+    pqb200_rep_fill_25(g_rep_launch);
+    pqb200_rep_fill_31(g_rep_launch);
+    pqb200_rep_fill_36(g_rep_launch);
+    pqb200_rep_fill_40(g_rep_launch);
+    pqb200_rep_fill_43(g_rep_launch);
     g_tables_ready = true;
 }
 
@@ -119,6 +144,10 @@ int get_device(int dev, DeviceCtx** out) {
         CUDA_TRY(cudaMallocHost(&c.h_out, sizeof(double) * 4));
         CUDA_TRY(cudaEventCreate(&c.e0));
         CUDA_TRY(cudaEventCreate(&c.e1));
+        CUDA_TRY(cudaMalloc(&c.rep_table, 16 * (size_t)kMaxRepLen));
+        CUDA_TRY(cudaMalloc(&c.rep_base, 16 * 2 * (size_t)kMaxRepN));
+        CUDA_TRY(cudaMalloc(&c.rep_binom, sizeof(double) * kMaxRepN * kRepBinomStride));
+        CUDA_TRY(cudaMalloc(&c.rep_lowpar, 2 * sizeof(int)));
         for (int i = 0; i < kPlainTableSize; i++) c.occ[i] = 0;
         c.dev = dev;
     }
@@ -291,6 +320,10 @@ void pqb200_shutdown(void) {
         cudaFree(c.partials);
         cudaFree(c.counter);
         cudaFree(c.d_out);
+        cudaFree(c.rep_table);
+        cudaFree(c.rep_base);
+        cudaFree(c.rep_binom);
+        cudaFree(c.rep_lowpar);
         cudaFreeHost(c.h_out);
         cudaEventDestroy(c.e0);
         cudaEventDestroy(c.e1);
@@ -315,22 +348,11 @@ int pqb200_last_stats(pqb200_stats* out) {
     return PQB200_OK;
 }
 
-int pqb200_permanent(const double* a, size_t rows, size_t cols, size_t stride, int ndev,
-                     double out[2]) {
-    if (!out) return fail(PQB200_ERR_ARG, "output pointer is null");
-    if (rows != 0 && cols != 0) {
-        int rc = check_plain_args(a, rows, cols, stride);
-        if (rc) return rc;
-    }
-    std::lock_guard<std::mutex> lk(g_mu);
-    int used = 0;
-    // the library must be usable (CUDA present) even for the trivial cases: no silent CPU path
-    int rc = ensure_devices(ndev, &used);
-    if (rc) return rc;
-    g_stats = {0.0, 0.0, 0, used};
-    if (plain_edge_case(a, rows, cols, stride, out)) return PQB200_OK;
-
-    const int max_threads = g_devs[0].sm_count * kPlainThreads;  // refined per N below
+// perm of a rows x cols matrix (2 <= rows <= cols+1) over `used` devices; caller holds g_mu
+static int plain_multi_device(const double* a, size_t rows, size_t cols, size_t stride, int used,
+                              size_t scale_rows, double out[2]) {
+    int rc;
+    const int max_threads = g_devs[0].sm_count * kPlainThreads;
     PlainPlan pl = plan_plain((int)rows, (int)cols, max_threads, (unsigned long long)used);
     if ((unsigned long long)used > pl.nchunks) used = (int)pl.nchunks;
     std::vector<double> parts(4 * (size_t)used);
@@ -354,11 +376,99 @@ int pqb200_permanent(const double* a, size_t rows, size_t cols, size_t stride, i
     float ms = 0.f;
     CUDA_TRY(cudaSetDevice(g_devs[0].dev));
     CUDA_TRY(cudaEventElapsedTime(&ms, g_devs[0].e0, g_devs[0].e1));
-    g_stats.kernel_ms = ms;
-    g_stats.gray_steps = ldexp(1.0, (int)rows - 1);
-    g_stats.launches = (uint64_t)used;
+    g_stats.kernel_ms += ms;
+    g_stats.gray_steps += ldexp(1.0, (int)rows - 1);
+    g_stats.launches += (uint64_t)used;
     g_stats.ndev = used;
-    combine_partials(parts.data(), (size_t)used, rows, out);
+    combine_partials(parts.data(), (size_t)used, scale_rows, out);
+    return PQB200_OK;
+}
+
+int pqb200_permanent(const double* a, size_t rows, size_t cols, size_t stride, int ndev,
+                     double out[2]) {
+    if (!out) return fail(PQB200_ERR_ARG, "output pointer is null");
+    if (rows != 0 && cols != 0) {
+        int rc = check_plain_args(a, rows, cols, stride);
+        if (rc) return rc;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    int used = 0;
+    // the library must be usable (CUDA present) even for the trivial cases: no silent CPU path
+    int rc = ensure_devices(ndev, &used);
+    if (rc) return rc;
+    g_stats = {0.0, 0.0, 0, used};
+    if (plain_edge_case(a, rows, cols, stride, out)) return PQB200_OK;
+    return plain_multi_device(a, rows, cols, stride, used, rows, out);
+}
+
+// one repeated-row permanent over `used` devices; caller holds g_mu
+static int repeated_locked(const double* a, size_t rows, size_t cols, size_t stride,
+                           const int64_t* row_mult, const int64_t* col_mult, int used, double out[2]) {
+    RepPrepared pr;
+    std::string err;
+    int rc = rep_prepare(a, rows, cols, stride, row_mult, col_mult, kMaxRepN, pr, err);
+    if (rc) return fail(rc, err);
+    if (pr.trivial) {
+        out[0] = pr.value[0];
+        out[1] = pr.value[1];
+        return PQB200_OK;
+    }
+    if (pr.all_single)  // every digit is binary: this is a plain permanent of the expanded matrix
+        return plain_multi_device(pr.mat.data(), (size_t)pr.R, (size_t)pr.N, (size_t)pr.N, used,
+                                  (size_t)pr.photons, out);
+    RepPlan pl;
+    rep_plan(pr, g_devs[0].sm_count * kPlainThreads, (unsigned long long)used, kMaxRepLen,
+             kRepBinomStride, pl);
+    if ((unsigned long long)used > pl.nchunks) used = (int)pl.nchunks;
+    std::vector<double> parts(4 * (size_t)used);
+    static_assert(sizeof(RepStepHost) == 16, "step table layout");
+    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
+    CUDA_TRY(cudaEventRecord(g_devs[0].e0, g_devs[0].stream));
+    for (int d = 0; d < used; d++) {
+        DeviceCtx& c = g_devs[d];
+        CUDA_TRY(cudaSetDevice(c.dev));
+        CUDA_TRY(cudaMemcpyAsync(c.rep_table, pl.table.data(), 16 * (size_t)pl.len, cudaMemcpyHostToDevice, c.stream));
+        CUDA_TRY(cudaMemcpyAsync(c.rep_base, pl.base.data(), 16 * 2 * (size_t)pr.N, cudaMemcpyHostToDevice, c.stream));
+        CUDA_TRY(cudaMemcpyAsync(c.rep_binom, pl.binom.data(), sizeof(double) * pl.binom.size(), cudaMemcpyHostToDevice, c.stream));
+        CUDA_TRY(cudaMemcpyAsync(c.rep_lowpar, pl.low_parity, 2 * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+        RepLaunchArgs x;
+        x.mat = pr.mat.data();
+        x.R = pr.R;
+        x.N = pr.N;
+        x.q = pl.q;
+        x.len = pl.len;
+        x.chunk_begin = pl.nchunks * (unsigned long long)d / (unsigned long long)used;
+        x.chunk_end = pl.nchunks * (unsigned long long)(d + 1) / (unsigned long long)used;
+        const unsigned long long want = (x.chunk_end - x.chunk_begin + kPlainThreads - 1) / kPlainThreads;
+        x.grid = (int)std::min<unsigned long long>(want, (unsigned long long)std::min(kMaxGridBlocks, c.sm_count));
+        x.radix = pl.radix;
+        x.weight = pl.weight;
+        x.table = c.rep_table;
+        x.base = c.rep_base;
+        x.binom = c.rep_binom;
+        x.low_parity = c.rep_lowpar;
+        x.partials = c.partials;
+        x.counter = c.counter;
+        x.out = c.d_out;
+        x.stream = c.stream;
+        CUDA_TRY(g_rep_launch[pr.N](x));
+        CUDA_TRY(cudaMemcpyAsync(c.h_out, c.d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        if (d == 0) CUDA_TRY(cudaEventRecord(c.e1, c.stream));
+    }
+    for (int d = 0; d < used; d++) {
+        DeviceCtx& c = g_devs[d];
+        CUDA_TRY(cudaSetDevice(c.dev));
+        CUDA_TRY(cudaStreamSynchronize(c.stream));  // also keeps pl / pr alive until the copies are done
+        memcpy(&parts[4 * (size_t)d], c.h_out, 4 * sizeof(double));
+    }
+    float ms = 0.f;
+    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
+    CUDA_TRY(cudaEventElapsedTime(&ms, g_devs[0].e0, g_devs[0].e1));
+    g_stats.kernel_ms += ms;
+    g_stats.gray_steps += (double)pl.nchunks * (double)pl.len;
+    g_stats.launches += (uint64_t)used;
+    g_stats.ndev = used;
+    combine_partials(parts.data(), (size_t)used, (size_t)pr.photons, out);
     return PQB200_OK;
 }
 
@@ -417,18 +527,45 @@ int pqb200_permanent_batch(const double* const* a, const size_t* rows, const siz
     return PQB200_OK;
 }
 
+static int check_repeated_args(const double* a, size_t rows, size_t cols, size_t stride,
+                               const int64_t* row_mult, const int64_t* col_mult) {
+    if ((rows && !row_mult) || (cols && !col_mult)) return fail(PQB200_ERR_ARG, "multiplicity pointer is null");
+    if (rows && cols && !a) return fail(PQB200_ERR_ARG, "matrix pointer is null");
+    if (rows && cols && stride < cols) return fail(PQB200_ERR_ARG, "stride is smaller than the number of columns");
+    return PQB200_OK;
+}
+
 int pqb200_permanent_repeated(const double* a, size_t rows, size_t cols, size_t stride,
                               const int64_t* row_mult, const int64_t* col_mult, int ndev,
                               double out[2]) {
-    (void)a; (void)rows; (void)cols; (void)stride; (void)row_mult; (void)col_mult; (void)ndev; (void)out;
-    return fail(PQB200_ERR_ARG, "pqb200_permanent_repeated: not built yet");
+    if (!out) return fail(PQB200_ERR_ARG, "output pointer is null");
+    int rc = check_repeated_args(a, rows, cols, stride, row_mult, col_mult);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_mu);
+    int used = 0;
+    rc = ensure_devices(ndev, &used);
+    if (rc) return rc;
+    g_stats = {0.0, 0.0, 0, used};
+    return repeated_locked(a, rows, cols, stride, row_mult, col_mult, used, out);
 }
 
 int pqb200_permanent_repeated_batch(const double* a, size_t rows, size_t cols, size_t stride,
                                     const int64_t* row_mults, const int64_t* col_mults,
                                     size_t count, int ndev, double* out) {
-    (void)a; (void)rows; (void)cols; (void)stride; (void)row_mults; (void)col_mults; (void)count; (void)ndev; (void)out;
-    return fail(PQB200_ERR_ARG, "pqb200_permanent_repeated_batch: not built yet");
+    if (count && !out) return fail(PQB200_ERR_ARG, "output pointer is null");
+    std::lock_guard<std::mutex> lk(g_mu);
+    int used = 0;
+    int rc = ensure_devices(ndev, &used);
+    if (rc) return rc;
+    g_stats = {0.0, 0.0, 0, used};
+    for (size_t k = 0; k < count; k++) {
+        rc = check_repeated_args(a, rows, cols, stride, row_mults + k * rows, col_mults + k * cols);
+        if (rc) return rc;
+        // first cut: one launch per state pair; the batched small-permanent kernel replaces this loop
+        rc = repeated_locked(a, rows, cols, stride, row_mults + k * rows, col_mults + k * cols, 1, out + 2 * k);
+        if (rc) return rc;
+    }
+    return PQB200_OK;
 }
 
 int pqb200_pmf_layer(const double* u, size_t m, size_t stride, const int64_t* samples,

@@ -1,0 +1,239 @@
+// repeated_host.h -- host-side preparation of a repeated-row permanent for glynn_repeated_kernel:
+// the reference's filtering / anchor-row step, the orientation choice, the physical expansion of
+// the product side, and the per-chunk step table (toggled row, direction for both high parities,
+// signed binomial weight).  Pure integer / table work; all floating-point summation happens on the
+// GPU except the two `base` vectors (sums of at most D rows, formed in long double).
+#pragma once
+#include <stdint.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "launch.h"
+
+namespace pqb200 {
+
+struct RepPrepared {
+    bool trivial = false;  // result already in `value`
+    double value[2] = {1.0, 0.0};
+    bool all_single = false;  // every digit has radix 2: use the plain kernel on `mat`
+    int N = 0;                // physically repeated columns (= total photons)
+    int R = 0;                // rows of `mat` including the anchor row 0
+    std::vector<double> mat;  // R x N complex, interleaved, row-major
+    std::vector<int> r;       // r[d] = multiplicity of row d+1, d = 0..R-2 (all >= 1)
+    int photons = 0;
+};
+
+// Reference semantics: BBFGPermanentCalculatorRepeated.cpp:74-141 and .hpp:74-140.
+//   returns 0 ok, 3 photon-number mismatch, 2 bad argument (message in err)
+inline int rep_prepare(const double* a, size_t rows, size_t cols, size_t stride,
+                       const int64_t* row_mult, const int64_t* col_mult, int max_n,
+                       RepPrepared& out, std::string& err) {
+    int64_t sr = 0, sc = 0;
+    for (size_t i = 0; i < rows; i++) {
+        if (row_mult[i] < 0) { err = "negative row multiplicity"; return 2; }
+        sr += row_mult[i];
+    }
+    for (size_t j = 0; j < cols; j++) {
+        if (col_mult[j] < 0) { err = "negative column multiplicity"; return 2; }
+        sc += col_mult[j];
+    }
+    if (sr != sc) {
+        err = "BBFGPermanentCalculatorRepeated_Tasks::calculate:  Number of input and output states should be equal";
+        return 3;
+    }
+    if (rows == 0 || cols == 0 || sr == 0) {  // hpp:126-128: empty permanent is 1
+        out.trivial = true;
+        return 0;
+    }
+    if (sr > max_n) {
+        err = "total photon number exceeds the limit of this build (" + std::to_string(max_n) + ")";
+        return 2;
+    }
+    // keep rows / columns with non-zero multiplicity (adaptInterferometer, BatchedPermanentCalculator.cpp:412-451)
+    std::vector<int> ri, ci;
+    for (size_t i = 0; i < rows; i++) if (row_mult[i] > 0) ri.push_back((int)i);
+    for (size_t j = 0; j < cols; j++) if (col_mult[j] > 0) ci.push_back((int)j);
+    // orientation: perm(A) = perm(A^T); index the Gray space by the side with the smaller
+    // prod(mult+1) (precedent: GlynnPermanentCalculatorRepeatedDFE.cpp:1138); ties keep rows.
+    auto space = [](const std::vector<int>& idx, const int64_t* mult) {
+        double s = 1.0;
+        int64_t mn = INT64_MAX;
+        for (int i : idx) { s *= (double)(mult[i] + 1); mn = std::min(mn, mult[i]); }
+        return s * (double)mn / (double)(mn + 1);  // the anchor takes one copy of a min-multiplicity row
+    };
+    const bool transpose = space(ci, col_mult) < space(ri, row_mult);
+    const std::vector<int>& gi = transpose ? ci : ri;    // Gray side indices
+    const std::vector<int>& pi = transpose ? ri : ci;    // product side indices
+    const int64_t* gm = transpose ? col_mult : row_mult;
+    const int64_t* pm = transpose ? row_mult : col_mult;
+    auto elem = [&](int g, int p, int part) {
+        const size_t i = transpose ? (size_t)p : (size_t)g, j = transpose ? (size_t)g : (size_t)p;
+        return a[2 * (i * stride + j) + part];
+    };
+    // anchor: the Gray-side row with the smallest non-zero multiplicity (first one on ties, hpp:78)
+    int amin = 0;
+    for (int k = 1; k < (int)gi.size(); k++)
+        if (gm[gi[k]] < gm[gi[amin]]) amin = k;
+    std::vector<int> grow;  // Gray-side rows of `mat` after the anchor
+    grow.push_back(gi[amin]);
+    out.r.clear();
+    for (int k = 0; k < (int)gi.size(); k++) {
+        const int m = (int)gm[gi[k]] - (k == amin ? 1 : 0);
+        if (m > 0) {
+            grow.push_back(gi[k]);
+            out.r.push_back(m);
+        }
+    }
+    out.photons = (int)sr;
+    out.N = (int)sr;
+    out.R = (int)grow.size();
+    out.mat.assign((size_t)out.R * out.N * 2, 0.0);
+    for (int i = 0; i < out.R; i++) {
+        int col = 0;
+        for (int p : pi)
+            for (int64_t rep = 0; rep < pm[p]; rep++) {
+                out.mat[2 * ((size_t)i * out.N + col)] = elem(grow[i], p, 0);
+                out.mat[2 * ((size_t)i * out.N + col) + 1] = elem(grow[i], p, 1);
+                col++;
+            }
+    }
+    if (out.R == 1) {  // single row: prod_j a_j^{c_j} (hpp:130-140)
+        double re = 1.0, im = 0.0;
+        for (int j = 0; j < out.N; j++) {
+            const double xr = out.mat[2 * j], xi = out.mat[2 * j + 1];
+            const double tr = re * xr - im * xi, ti = re * xi + im * xr;
+            re = tr;
+            im = ti;
+        }
+        out.trivial = true;
+        out.value[0] = re;
+        out.value[1] = im;
+        return 0;
+    }
+    out.all_single = std::all_of(out.r.begin(), out.r.end(), [](int m) { return m == 1; });
+    return 0;
+}
+
+struct RepStepHost {
+    double w;
+    int row;
+    unsigned int flags;
+};
+
+struct RepPlan {
+    int q = 0;
+    unsigned int len = 1;
+    unsigned long long nchunks = 1;
+    std::vector<RepStepHost> table;
+    std::vector<double> base;   // [2][N] complex interleaved
+    std::vector<double> binom;  // [D][stride]
+    int low_parity[2] = {0, 0};
+    unsigned long long weight[64];
+    unsigned char radix[64];
+};
+
+inline double binom_d(int r, int k) {
+    double c = 1.0;
+    for (int t = 1; t <= k; t++) c = c * (double)(r - k + t) / (double)t;  // exact: every prefix is an integer < 2^53
+    return c;
+}
+
+// Choose the number of low digits and build the per-step table for them.
+inline void rep_plan(const RepPrepared& pr, int max_resident_threads, unsigned long long shards,
+                     unsigned int max_len, int binom_stride, RepPlan& pl) {
+    const int D = pr.R - 1, N = pr.N;
+    for (int d = 0; d < D; d++) pl.radix[d] = (unsigned char)(pr.r[d] + 1);
+    double total = 1.0;
+    for (int d = 0; d < D; d++) total *= pl.radix[d];
+    // cost model: waves * (seed + len * step)
+    double best = 1e300;
+    int bestq = 0;
+    unsigned long long len = 1;
+    for (int q = 0; q <= D; q++) {
+        if (q > 0) len *= pl.radix[q - 1];
+        if (len > max_len) break;
+        const double chunks = total / (double)len;
+        const double per_shard = std::max(1.0, chunks / (double)shards);
+        const double threads = std::min((double)max_resident_threads, per_shard);
+        const double waves = (double)(unsigned long long)((per_shard + threads - 1) / threads);
+        const double cost = waves * ((D - q) * (2.0 * N + 60.0) + 2.0 * N + (double)len * (6.0 * N + 14.0));
+        if (cost < best) {
+            best = cost;
+            bestq = q;
+        }
+    }
+    pl.q = bestq;
+    pl.len = 1;
+    for (int d = 0; d < pl.q; d++) pl.len *= pl.radix[d];
+    pl.nchunks = 1;
+    for (int d = pl.q; d < D; d++) {
+        pl.weight[d] = pl.nchunks;
+        pl.nchunks *= pl.radix[d];
+    }
+    for (int d = 0; d < pl.q; d++) pl.weight[d] = 0;
+    // binomial table
+    pl.binom.assign((size_t)std::max(D, 1) * binom_stride, 0.0);
+    for (int d = 0; d < D; d++)
+        for (int k = 0; k <= pr.r[d]; k++) pl.binom[(size_t)d * binom_stride + k] = binom_d(pr.r[d], k);
+    // low digits: simulate the reflected mixed-radix counter for both high parities
+    const int q = pl.q;
+    std::vector<int> cnt(q, 0), g0(q, 0), g1(q, 0), n0(q), n1(q);
+    auto gray = [&](int P, std::vector<int>& g) {
+        int par = P;
+        for (int d = q - 1; d >= 0; d--) {
+            g[d] = par ? pr.r[d] - cnt[d] : cnt[d];
+            par ^= g[d] & 1;
+        }
+    };
+    gray(0, g0);
+    gray(1, g1);
+    pl.base.assign((size_t)2 * N * 2, 0.0);
+    for (int P = 0; P < 2; P++) {
+        const std::vector<int>& g = P ? g1 : g0;
+        int ks = 0;
+        for (int d = 0; d < q; d++) ks += g[d];
+        pl.low_parity[P] = ks & 1;
+        for (int j = 0; j < N; j++) {
+            long double re = pr.mat[2 * j], im = pr.mat[2 * j + 1];
+            for (int d = 0; d < q; d++) {
+                const long double coef = (long double)(pr.r[d] - 2 * g[d]);
+                re += coef * (long double)pr.mat[2 * ((size_t)(d + 1) * N + j)];
+                im += coef * (long double)pr.mat[2 * ((size_t)(d + 1) * N + j) + 1];
+            }
+            pl.base[2 * ((size_t)P * N + j)] = (double)re;
+            pl.base[2 * ((size_t)P * N + j) + 1] = (double)im;
+        }
+    }
+    pl.table.assign(pl.len, RepStepHost{1.0, 0, 0u});
+    auto weight_of = [&](const std::vector<int>& g) {
+        double w = 1.0;
+        for (int d = 0; d < q; d++) w *= pl.binom[(size_t)d * binom_stride + g[d]];
+        return w;
+    };
+    pl.table[0].w = weight_of(g0);
+    for (unsigned int t = 1; t < pl.len; t++) {
+        int d = 0;
+        for (;;) {  // n_aryGrayCodeCounter::next, n_aryGrayCodeCounter.cpp:203-216
+            if (cnt[d] < pr.r[d]) { cnt[d]++; break; }
+            cnt[d] = 0;
+            d++;
+        }
+        gray(0, n0);
+        gray(1, n1);
+        int ch = -1;
+        for (int e = 0; e < q; e++)
+            if (n0[e] != g0[e]) ch = e;
+        unsigned int flags = 0;
+        if (n0[ch] > g0[ch]) flags |= 1u;
+        if (n1[ch] > g1[ch]) flags |= 2u;
+        g0 = n0;
+        g1 = n1;
+        pl.table[t].row = ch + 1;
+        pl.table[t].flags = flags;
+        pl.table[t].w = ((t & 1u) ? -1.0 : 1.0) * weight_of(g0);
+    }
+}
+
+}  // namespace pqb200
