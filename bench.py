@@ -3,7 +3,7 @@
 its 2^(n-1) Gray steps sharded over the N GPUs of one node (one process per GPU under torchrun),
 partials combined with one NCCL all-gather of 4 doubles per rank.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--n 40] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--size 40] [--impl b200|reference]
 
 Prints ONE JSON line (rank 0).  `value` = Gray steps per second of the whole job (inputs resident:
 the matrix travels as 25.6 KB of kernel parameters, there is nothing else to stage); `e2e` = the same
@@ -289,7 +289,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=40, help="matrix size (BASELINE config C3 = 40)")
+    ap.add_argument("--size", dest="n", type=int, default=40, help="matrix size (BASELINE config C3 = 40)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
     ap.add_argument("--ref-step-seconds", type=float, default=6.0, help="--impl reference: per-step budget")
     args = ap.parse_args()
