@@ -99,6 +99,16 @@ int pqb200_permanent_repeated_batch(const double* a, size_t rows, size_t cols, s
 int pqb200_pmf_layer(const double* u, size_t m, size_t stride, const int64_t* samples /* S x m */,
                      const int64_t* inputs /* S x m */, size_t S, int ndev, double* pmf /* S x m */);
 
+/* The lossless Clifford-Clifford "B" sampler: `shots` samples of the output occupation for the
+ * input occupation `input_state` behind interferometer U (m x m).  All shots advance through photon
+ * step k together (one pqb200_pmf_layer per step); the std::mt19937 stream is consumed in exactly the
+ * reference's order, so seeded runs reproduce the reference's shots.  Replaces
+ *   CGeneralizedCliffordsBSimulationStrategy::seed + simulate
+ *     sampling/simulation_strategies/source/CGeneralizedCliffordsBSimulationStrategy.cpp:113-116,137-316
+ * samples_out: shots x m, in the reference's C++ generation order. */
+int pqb200_simulate_B(const double* u, size_t m, size_t stride, const int64_t* input_state,
+                      size_t shots, uint64_t seed, int ndev, int64_t* samples_out);
+
 /* Timing of the most recent compute call on this thread (CUDA events around the kernels on device
  * 0 of the call): kernel milliseconds, Gray steps executed, kernels launched. */
 typedef struct pqb200_stats {

@@ -7,5 +7,10 @@ reference's own class names.  The compute lives in libpqb200.so (csrc/, C ABI in
 from . import _lib
 from ._lib import Pqb200Error, last_stats, load
 from .Boson_Sampling_Utilities import *  # noqa: F401,F403
+from .simulation_strategies import (  # noqa: F401
+    GeneralizedCliffordsBSimulationStrategy,
+    GeneralizedCliffordsBSimulationStrategy_wrapper,
+    compute_pmf,
+)
 
 __all__ = ["_lib", "Pqb200Error", "last_stats", "load"]

@@ -69,6 +69,11 @@ _SIGNATURES = {
         [c_double_p, ctypes.c_size_t, ctypes.c_size_t, c_int64_p, c_int64_p, ctypes.c_size_t,
          ctypes.c_int, c_double_p],
     ),
+    "pqb200_simulate_B": (
+        ctypes.c_int,
+        [c_double_p, ctypes.c_size_t, ctypes.c_size_t, c_int64_p, ctypes.c_size_t, ctypes.c_uint64,
+         ctypes.c_int, c_int64_p],
+    ),
     "pqb200_last_stats": (ctypes.c_int, [ctypes.POINTER(Pqb200Stats)]),
     "pqb200_fp64_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_double, c_double_p]),
 }

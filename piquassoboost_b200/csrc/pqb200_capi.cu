@@ -10,12 +10,14 @@
 
 #include <algorithm>
 #include <mutex>
+#include <random>
 #include <string>
 #include <vector>
 
 #include "../../include/pqb200.h"
 #include "dd.cuh"
 #include "launch.h"
+#include "batch_host.h"
 #include "repeated_host.h"
 
 using namespace pqb200;
@@ -62,6 +64,13 @@ struct DeviceCtx {
     void* rep_base = nullptr;
     double* rep_binom = nullptr;
     int* rep_lowpar = nullptr;
+    // batch path: growable device buffers (matrix data, job descriptors, results, pmf scratch)
+    void* b_u = nullptr;      size_t b_u_cap = 0;
+    void* b_jobs = nullptr;   size_t b_jobs_cap = 0;
+    void* b_out = nullptr;    size_t b_out_cap = 0;
+    void* b_weight = nullptr; size_t b_weight_cap = 0;
+    void* b_pmf = nullptr;    size_t b_pmf_cap = 0;
+    bool batch_ready = false;
 };
 
 std::mutex g_mu;
@@ -324,6 +333,11 @@ void pqb200_shutdown(void) {
         cudaFree(c.rep_base);
         cudaFree(c.rep_binom);
         cudaFree(c.rep_lowpar);
+        cudaFree(c.b_u);
+        cudaFree(c.b_jobs);
+        cudaFree(c.b_out);
+        cudaFree(c.b_weight);
+        cudaFree(c.b_pmf);
         cudaFreeHost(c.h_out);
         cudaEventDestroy(c.e0);
         cudaEventDestroy(c.e1);
@@ -516,13 +530,70 @@ int pqb200_permanent_combine(const double* partials_dd, size_t count, size_t row
     return PQB200_OK;
 }
 
-int pqb200_permanent_batch(const double* const* a, const size_t* rows, const size_t* cols,
-                           const size_t* strides, size_t count, int ndev, double* out) {
-    if (!out || (count && (!a || !rows || !cols || !strides))) return fail(PQB200_ERR_ARG, "null pointer");
-    // first cut: one launch per matrix; the batched small-matrix kernel replaces this loop
-    for (size_t k = 0; k < count; k++) {
-        int rc = pqb200_permanent(a[k], rows[k], cols[k], strides[k], ndev, out + 2 * k);
-        if (rc) return rc;
+static int grow(void** p, size_t* cap, size_t need) {
+    if (need <= *cap) return PQB200_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    const size_t want = std::max(need, (size_t)1 << 16) * 3 / 2;
+    CUDA_TRY(cudaMalloc(p, want));
+    *cap = want;
+    return PQB200_OK;
+}
+
+struct BatchItem {
+    BatchJobHost job;
+    BatchJobKind kind;
+};
+
+// single-row job: prod_j U[g][p_j] on the host (the reference's rows == 1 branch, hpp:130-140)
+static void single_row_value(const double* u, size_t ustride, const BatchJobHost& j, double out[2]) {
+    double re = 1.0, im = 0.0;
+    for (int c = 0; c < j.N; c++) {
+        const size_t g = j.gidx[0], pc = j.pidx[c];
+        const size_t off = j.transpose ? (pc * ustride + g) : (g * ustride + pc);
+        const double xr = u[2 * off], xi = u[2 * off + 1];
+        const double tr = re * xr - im * xi, ti = re * xi + im * xr;
+        re = tr;
+        im = ti;
+    }
+    out[0] = re;
+    out[1] = im;
+}
+
+// Runs the kernel jobs of `items` (all referring to matrix data already resident in c.b_u) on device
+// c and leaves their results in c.b_out[out_slot]; trivial kinds must have been pre-filled by the
+// caller in `prefill` (count x complex), which is uploaded first.  Async on c.stream.
+static int run_batch_on_device(DeviceCtx& c, const std::vector<BatchItem>& items,
+                               const std::vector<double>& prefill, size_t nslots) {
+    CUDA_TRY(cudaSetDevice(c.dev));
+    if (!c.batch_ready) {
+        CUDA_TRY(batch_init_device());
+        c.batch_ready = true;
+    }
+    int rc = grow(&c.b_out, &c.b_out_cap, 16 * std::max<size_t>(nslots, 1));
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c.b_out, prefill.data(), 16 * nslots, cudaMemcpyHostToDevice, c.stream));
+    // group the kernel jobs by column bucket
+    std::vector<std::vector<BatchJobHost>> buckets(64);
+    for (const BatchItem& it : items)
+        if (it.kind == kJobKernel) buckets[(size_t)batch_bucket(it.job.N)].push_back(it.job);
+    std::vector<BatchJobHost> flat;
+    std::vector<std::pair<int, std::pair<size_t, size_t>>> launches;  // bucket, (offset, count)
+    for (int b = 0; b < 64; b++)
+        if (!buckets[b].empty()) {
+            launches.push_back({b, {flat.size(), buckets[b].size()}});
+            flat.insert(flat.end(), buckets[b].begin(), buckets[b].end());
+        }
+    if (flat.empty()) return PQB200_OK;
+    rc = grow(&c.b_jobs, &c.b_jobs_cap, sizeof(BatchJobHost) * flat.size());
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c.b_jobs, flat.data(), sizeof(BatchJobHost) * flat.size(), cudaMemcpyHostToDevice, c.stream));
+    CUDA_TRY(cudaStreamSynchronize(c.stream));  // `flat` and `prefill` are host temporaries
+    for (auto& l : launches) {
+        CUDA_TRY(batch_launch(l.first, c.b_u, (const char*)c.b_jobs + sizeof(BatchJobHost) * l.second.first,
+                              (int)l.second.second, c.b_out, c.stream));
+        g_stats.launches += 1;
     }
     return PQB200_OK;
 }
@@ -553,25 +624,296 @@ int pqb200_permanent_repeated_batch(const double* a, size_t rows, size_t cols, s
                                     const int64_t* row_mults, const int64_t* col_mults,
                                     size_t count, int ndev, double* out) {
     if (count && !out) return fail(PQB200_ERR_ARG, "output pointer is null");
+    if (count == 0) return PQB200_OK;
     std::lock_guard<std::mutex> lk(g_mu);
     int used = 0;
     int rc = ensure_devices(ndev, &used);
     if (rc) return rc;
     g_stats = {0.0, 0.0, 0, used};
+    std::vector<BatchItem> items(count);
+    std::vector<double> prefill(2 * count, 0.0);
+    std::vector<size_t> too_big;
     for (size_t k = 0; k < count; k++) {
         rc = check_repeated_args(a, rows, cols, stride, row_mults + k * rows, col_mults + k * cols);
         if (rc) return rc;
-        // first cut: one launch per state pair; the batched small-permanent kernel replaces this loop
-        rc = repeated_locked(a, rows, cols, stride, row_mults + k * rows, col_mults + k * cols, 1, out + 2 * k);
+        std::string err;
+        BatchItem& it = items[k];
+        memset(&it.job, 0, sizeof(it.job));
+        rc = make_batch_job(rows, cols, row_mults + k * rows, col_mults + k * cols, it.job, it.kind, err);
+        if (rc) return fail(rc, err);
+        it.job.out_slot = (int)k;
+        it.job.ustride = (int)stride;
+        it.job.uoff = 0;
+        if (it.kind == kJobTrivialOne) prefill[2 * k] = 1.0;
+        else if (it.kind == kJobSingleRow) single_row_value(a, stride, it.job, &prefill[2 * k]);
+        else if (it.kind == kJobTooBig) too_big.push_back(k);
+    }
+    // shard the items over the devices by contiguous ranges
+    used = (int)std::min<size_t>((size_t)used, count);
+    std::vector<std::vector<BatchItem>> per_dev((size_t)used);
+    for (size_t k = 0; k < count; k++) per_dev[k * (size_t)used / count].push_back(items[k]);
+    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
+    CUDA_TRY(cudaEventRecord(g_devs[0].e0, g_devs[0].stream));
+    for (int d = 0; d < used; d++) {
+        DeviceCtx& c = g_devs[d];
+        CUDA_TRY(cudaSetDevice(c.dev));
+        rc = grow(&c.b_u, &c.b_u_cap, 16 * rows * stride);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c.b_u, a, 16 * ((rows - 1) * stride + cols), cudaMemcpyHostToDevice, c.stream));
+        rc = run_batch_on_device(c, per_dev[(size_t)d], prefill, count);
+        if (rc) return rc;
+        if (d == 0) CUDA_TRY(cudaEventRecord(c.e1, c.stream));
+    }
+    std::vector<double> res(2 * count);
+    for (int d = 0; d < used; d++) {
+        DeviceCtx& c = g_devs[d];
+        CUDA_TRY(cudaSetDevice(c.dev));
+        CUDA_TRY(cudaMemcpyAsync(res.data(), c.b_out, 16 * count, cudaMemcpyDeviceToHost, c.stream));
+        CUDA_TRY(cudaStreamSynchronize(c.stream));
+        for (const BatchItem& it : per_dev[(size_t)d]) {
+            out[2 * it.job.out_slot] = res[2 * it.job.out_slot];
+            out[2 * it.job.out_slot + 1] = res[2 * it.job.out_slot + 1];
+        }
+    }
+    float ms = 0.f;
+    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
+    CUDA_TRY(cudaEventElapsedTime(&ms, g_devs[0].e0, g_devs[0].e1));
+    g_stats.kernel_ms = ms;
+    // jobs whose Gray space is too large for one CTA use the grid-wide kernels, one at a time
+    for (size_t k : too_big) {
+        rc = repeated_locked(a, rows, cols, stride, row_mults + k * rows, col_mults + k * cols, used, out + 2 * k);
         if (rc) return rc;
     }
     return PQB200_OK;
 }
 
+int pqb200_permanent_batch(const double* const* a, const size_t* rows, const size_t* cols,
+                           const size_t* strides, size_t count, int ndev, double* out) {
+    if (!out || (count && (!a || !rows || !cols || !strides))) return fail(PQB200_ERR_ARG, "null pointer");
+    if (count == 0) return PQB200_OK;
+    std::vector<size_t> single;  // matrices that do not fit one CTA (or are not square): grid-wide path
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        int used = 0;
+        int rc = ensure_devices(ndev, &used);
+        if (rc) return rc;
+        g_stats = {0.0, 0.0, 0, used};
+        DeviceCtx& c = g_devs[0];  // small matrices: one device is plenty (launch-latency bound)
+        std::vector<BatchItem> items;
+        std::vector<double> prefill(2 * count, 0.0), packed;
+        const int64_t ones[kBatchColsMax] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
+                                             1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+        for (size_t k = 0; k < count; k++) {
+            const size_t n = rows[k];
+            if (n != cols[k] || n < 2 || n > 22) {
+                single.push_back(k);
+                continue;
+            }
+            rc = check_plain_args(a[k], n, n, strides[k]);
+            if (rc) return rc;
+            BatchItem it;
+            memset(&it.job, 0, sizeof(it.job));
+            std::string err;
+            rc = make_batch_job(n, n, ones, ones, it.job, it.kind, err);
+            if (rc) return fail(rc, err);
+            if (it.kind != kJobKernel) {
+                single.push_back(k);
+                continue;
+            }
+            it.job.out_slot = (int)k;
+            it.job.ustride = (int)n;
+            it.job.uoff = packed.size() / 2;
+            for (size_t i = 0; i < n; i++)
+                packed.insert(packed.end(), a[k] + 2 * i * strides[k], a[k] + 2 * (i * strides[k] + n));
+            items.push_back(it);
+        }
+        if (!items.empty()) {
+            CUDA_TRY(cudaSetDevice(c.dev));
+            rc = grow(&c.b_u, &c.b_u_cap, sizeof(double) * packed.size());
+            if (rc) return rc;
+            CUDA_TRY(cudaEventRecord(c.e0, c.stream));
+            CUDA_TRY(cudaMemcpyAsync(c.b_u, packed.data(), sizeof(double) * packed.size(), cudaMemcpyHostToDevice, c.stream));
+            rc = run_batch_on_device(c, items, prefill, count);
+            if (rc) return rc;
+            CUDA_TRY(cudaEventRecord(c.e1, c.stream));
+            std::vector<double> res(2 * count);
+            CUDA_TRY(cudaMemcpyAsync(res.data(), c.b_out, 16 * count, cudaMemcpyDeviceToHost, c.stream));
+            CUDA_TRY(cudaStreamSynchronize(c.stream));
+            for (const BatchItem& it : items) {
+                out[2 * it.job.out_slot] = res[2 * it.job.out_slot];
+                out[2 * it.job.out_slot + 1] = res[2 * it.job.out_slot + 1];
+            }
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, c.e0, c.e1));
+            g_stats.kernel_ms = ms;
+        }
+    }
+    for (size_t k : single) {
+        int rc = pqb200_permanent(a[k], rows[k], cols[k], strides[k], ndev, out + 2 * k);
+        if (rc) return rc;
+    }
+    return PQB200_OK;
+}
+
+// pmf rows for shots [s0, s1) on device c; async on c.stream, results left in c.b_pmf
+static int pmf_layer_on_device(DeviceCtx& c, const double* u, size_t m, size_t stride,
+                               const int64_t* samples, const int64_t* inputs, size_t s0, size_t s1,
+                               std::vector<std::pair<size_t, std::vector<int64_t>>>& too_big) {
+    const size_t S = s1 - s0;
+    std::vector<BatchItem> items;
+    std::vector<double> prefill(2 * S * m, 0.0), weight(S * m, 0.0);
+    std::vector<int64_t> cols(m);
+    for (size_t s = s0; s < s1; s++) {
+        const int64_t* sample = samples + s * m;
+        const int64_t* input = inputs + s * m;
+        for (size_t i = 0; i < m; i++) {
+            if (input[i] <= 0) continue;
+            weight[(s - s0) * m + i] = (double)input[i];
+            memcpy(cols.data(), input, m * sizeof(int64_t));
+            cols[i]--;  // input_loc = current_input - e_i (samplingHelperFunctions.cpp:139-143)
+            BatchItem it;
+            memset(&it.job, 0, sizeof(it.job));
+            std::string err;
+            int rc = make_batch_job(m, m, sample, cols.data(), it.job, it.kind, err);
+            if (rc) return fail(rc, err);
+            const size_t slot = (s - s0) * m + i;
+            it.job.out_slot = (int)slot;
+            it.job.ustride = (int)stride;
+            it.job.uoff = 0;
+            if (it.kind == kJobTrivialOne) prefill[2 * slot] = 1.0;
+            else if (it.kind == kJobSingleRow) single_row_value(u, stride, it.job, &prefill[2 * slot]);
+            else if (it.kind == kJobTooBig) {
+                // grid-wide kernels, synchronously, before this device's batch is enqueued
+                double v[2];
+                rc = repeated_locked(u, m, m, stride, sample, cols.data(), 1, v);
+                if (rc) return rc;
+                prefill[2 * slot] = v[0];
+                prefill[2 * slot + 1] = v[1];
+            } else {
+                items.push_back(it);
+            }
+        }
+    }
+    (void)too_big;
+    CUDA_TRY(cudaSetDevice(c.dev));
+    int rc = grow(&c.b_u, &c.b_u_cap, 16 * m * stride);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c.b_u, u, 16 * ((m - 1) * stride + m), cudaMemcpyHostToDevice, c.stream));
+    rc = grow(&c.b_weight, &c.b_weight_cap, sizeof(double) * S * m);
+    if (rc) return rc;
+    rc = grow(&c.b_pmf, &c.b_pmf_cap, sizeof(double) * S * m);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c.b_weight, weight.data(), sizeof(double) * S * m, cudaMemcpyHostToDevice, c.stream));
+    rc = run_batch_on_device(c, items, prefill, S * m);  // synchronises the uploads of the host temporaries
+    if (rc) return rc;
+    CUDA_TRY(pmf_combine_launch(c.b_u, (int)stride, (int)m, c.b_out, (const double*)c.b_weight,
+                                (double*)c.b_pmf, (int)S, c.stream));
+    g_stats.launches += 1;
+    return PQB200_OK;
+}
+
+// caller holds g_mu
+static int pmf_layer_locked(const double* u, size_t m, size_t stride, const int64_t* samples,
+                            const int64_t* inputs, size_t S, int used, double* pmf) {
+    used = (int)std::min<size_t>((size_t)used, S);
+    std::vector<std::pair<size_t, std::vector<int64_t>>> too_big;
+    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
+    CUDA_TRY(cudaEventRecord(g_devs[0].e0, g_devs[0].stream));
+    for (int d = 0; d < used; d++) {
+        const size_t s0 = S * (size_t)d / (size_t)used, s1 = S * (size_t)(d + 1) / (size_t)used;
+        int rc = pmf_layer_on_device(g_devs[d], u, m, stride, samples, inputs, s0, s1, too_big);
+        if (rc) return rc;
+        if (d == 0) CUDA_TRY(cudaEventRecord(g_devs[0].e1, g_devs[0].stream));
+    }
+    for (int d = 0; d < used; d++) {
+        DeviceCtx& c = g_devs[d];
+        const size_t s0 = S * (size_t)d / (size_t)used, s1 = S * (size_t)(d + 1) / (size_t)used;
+        CUDA_TRY(cudaSetDevice(c.dev));
+        CUDA_TRY(cudaMemcpyAsync(pmf + s0 * m, c.b_pmf, sizeof(double) * (s1 - s0) * m, cudaMemcpyDeviceToHost, c.stream));
+        CUDA_TRY(cudaStreamSynchronize(c.stream));
+    }
+    float ms = 0.f;
+    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
+    CUDA_TRY(cudaEventElapsedTime(&ms, g_devs[0].e0, g_devs[0].e1));
+    g_stats.kernel_ms += ms;
+    g_stats.ndev = used;
+    return PQB200_OK;
+}
+
 int pqb200_pmf_layer(const double* u, size_t m, size_t stride, const int64_t* samples,
                      const int64_t* inputs, size_t S, int ndev, double* pmf) {
-    (void)u; (void)m; (void)stride; (void)samples; (void)inputs; (void)S; (void)ndev; (void)pmf;
-    return fail(PQB200_ERR_ARG, "pqb200_pmf_layer: not built yet");
+    if (!u || !samples || !inputs || !pmf) return fail(PQB200_ERR_ARG, "null pointer");
+    if (m == 0 || m > 255) return fail(PQB200_ERR_ARG, "number of modes must be in 1..255");
+    if (stride < m) return fail(PQB200_ERR_ARG, "stride is smaller than the number of modes");
+    if (S == 0) return PQB200_OK;
+    std::lock_guard<std::mutex> lk(g_mu);
+    int used = 0;
+    int rc = ensure_devices(ndev, &used);
+    if (rc) return rc;
+    g_stats = {0.0, 0.0, 0, used};
+    return pmf_layer_locked(u, m, stride, samples, inputs, S, used, pmf);
+}
+
+int pqb200_simulate_B(const double* u, size_t m, size_t stride, const int64_t* input_state,
+                      size_t shots, uint64_t seed, int ndev, int64_t* samples_out) {
+    if (!u || !input_state || (shots && !samples_out)) return fail(PQB200_ERR_ARG, "null pointer");
+    if (m == 0 || m > 255) return fail(PQB200_ERR_ARG, "number of modes must be in 1..255");
+    if (stride < m) return fail(PQB200_ERR_ARG, "stride is smaller than the number of modes");
+    int64_t nphot = 0;
+    for (size_t i = 0; i < m; i++) {
+        if (input_state[i] < 0) return fail(PQB200_ERR_ARG, "negative occupation number");
+        nphot += input_state[i];
+    }
+    if (shots == 0) return PQB200_OK;
+    std::lock_guard<std::mutex> lk(g_mu);
+    int used = 0;
+    int rc = ensure_devices(ndev, &used);
+    if (rc) return rc;
+    g_stats = {0.0, 0.0, 0, used};
+    // The reference draws exactly two numbers per photon step per shot from ONE std::mt19937, shot
+    // after shot (samplingHelperFunctions.cpp:58-74,355,389): pre-generate them in that order so
+    // that all shots can advance through photon step k together.
+    std::mt19937 rng(static_cast<std::mt19937::result_type>(seed));
+    std::vector<uint32_t> draws(shots * 2 * (size_t)nphot);
+    for (auto& d : draws) d = (uint32_t)rng();
+    std::vector<int64_t> cur(shots * m, 0), work(shots * m);
+    for (size_t s = 0; s < shots; s++) memcpy(&work[s * m], input_state, m * sizeof(int64_t));
+    memset(samples_out, 0, shots * m * sizeof(int64_t));
+    std::vector<double> pmf(shots * m);
+    for (int64_t k = 0; k < nphot; k++) {
+        const uint32_t left = (uint32_t)(nphot - k);
+        for (size_t s = 0; s < shots; s++) {
+            // update_input_by_single_photon (samplingHelperFunctions.cpp:377-406): the
+            // (rng() % left)-th not-yet-inserted photon, photons listed in mode order
+            uint32_t pick = draws[(s * (size_t)nphot + (size_t)k) * 2] % left;
+            int64_t* w = &work[s * m];
+            for (size_t i = 0; i < m; i++) {
+                if ((int64_t)pick < w[i]) {
+                    w[i]--;
+                    cur[s * m + i]++;
+                    break;
+                }
+                pick -= (uint32_t)w[i];
+            }
+        }
+        rc = pmf_layer_locked(u, m, stride, samples_out, cur.data(), shots, used, pmf.data());
+        if (rc) return rc;
+        for (size_t s = 0; s < shots; s++) {
+            // sample_from_pmf (samplingHelperFunctions.cpp:350-374)
+            const double r = (double)draws[(s * (size_t)nphot + (size_t)k) * 2 + 1] / 4294967295.0;
+            size_t chosen = 0;
+            double acc = 0.0;
+            for (size_t i = 0; i < m; i++) {
+                acc += pmf[s * m + i];
+                if (acc >= r) {
+                    chosen = i;
+                    break;
+                }
+            }
+            samples_out[s * m + chosen]++;
+        }
+    }
+    return PQB200_OK;
 }
 
 }  // extern "C"

@@ -1,0 +1,84 @@
+"""GPU parity tests of the batched sub-permanent path: pmf layer and the Clifford-Clifford B sampler
+against the reference's seeded golden shots (unittests/test_seeding.py) and compute_pmf rows."""
+import numpy as np
+import pytest
+
+import golden_util as G
+from conftest import haar_unitary, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pqb():
+    import piquassoboost_b200 as p
+    p.load()
+    return p
+
+
+def test_pmf_rows_match_reference_golden(pqb):
+    g = G.load("sampling_seed123.json")
+    U = G.mat(g["U"])
+    for row in g["pmf_rows"]:
+        pmf = pqb.compute_pmf(U, row["sample"], row["current_input"])
+        assert np.allclose(pmf, row["pmf"], rtol=1e-11, atol=1e-15), row
+        assert abs(pmf.sum() - 1) < 1e-13
+
+
+def test_seeded_sampler_reproduces_reference_shots(pqb):
+    """seed 123, input [2,1,1,0,1], 20 shots: exact equality with the C++ generation order of the
+    unmodified reference, and multiset equality with unittests/test_seeding.py:62-83."""
+    g = G.load("sampling_seed123.json")
+    U = G.mat(g["U"])
+    strat = pqb.GeneralizedCliffordsBSimulationStrategy(U, seed=g["seed"])
+    shots = strat.simulate(np.array(g["input"], dtype=np.int64), g["shots"])
+    assert isinstance(shots, tuple) and len(shots) == g["shots"]
+    got = [s.tolist() for s in shots]
+    assert got == g["cpp_generation_order"]
+    assert sorted(map(tuple, got)) == sorted(map(tuple, g["expected_python_order"]))
+
+
+def test_pmf_layer_many_shots_vs_oracle(pqb, ref):
+    rng = np.random.default_rng(3)
+    m, k = 9, 6
+    U = haar_unitary(m, 17)
+    S = 40
+    samples = np.zeros((S, m), dtype=np.int64)
+    inputs = np.zeros((S, m), dtype=np.int64)
+    for s in range(S):
+        samples[s] = rng.multinomial(k - 1, [1 / m] * m)
+        inputs[s] = rng.multinomial(k, [1 / m] * m)
+    pmf = pqb.compute_pmf(U, samples, inputs)
+    for s in range(S):
+        want = ref.compute_pmf(U, samples[s], inputs[s])
+        assert np.allclose(pmf[s], want, rtol=1e-10, atol=1e-14), s
+
+
+def test_sampler_larger_instance_matches_oracle_shots(pqb, ref):
+    # 8 photons in 12 modes, 25 shots: identical shots to the unmodified reference sampler
+    U = haar_unitary(12, 4)
+    inp = np.array([1, 1, 0, 2, 0, 1, 0, 1, 1, 0, 1, 0], dtype=np.int64)
+    want = ref.simulate_B(U, 77, inp, 25)
+    got = np.array(pqb.GeneralizedCliffordsBSimulationStrategy(U, seed=77).simulate(inp, 25))
+    assert (got == want).all()
+    assert (got.sum(axis=1) == inp.sum()).all()
+
+
+def test_batch_of_small_plain_matrices(pqb, ref):
+    mats = [haar_unitary(n, 500 + n) for n in (2, 3, 5, 8, 11, 14, 17, 20, 7, 7)]
+    got = pqb.GlynnPermanentCalculator_wrapper(mats, 7).calculate()
+    for g_, m_ in zip(got, mats):
+        assert relerr(g_, ref.bbfg(m_, True)) < 1e-11
+
+
+def test_repeated_batch_many_states(pqb, ref):
+    rng = np.random.default_rng(8)
+    m = 10
+    U = haar_unitary(m, 9)
+    ins = [rng.multinomial(7, [1 / m] * m) for _ in range(12)]
+    outs = [rng.multinomial(7, [1 / m] * m) for _ in range(9)]
+    res = pqb.ChinHuhPermanentCalculator_wrapper(7, U, ins, outs).calculate()
+    for i, a in enumerate(ins):
+        for j, b in enumerate(outs):
+            want = ref.bbfg_repeated(U, a, b, True)
+            assert abs(res[i][j] - want) <= 1e-11 * max(abs(want), 1e-12), (i, j)
