@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "pqb200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(pqb200_[a-z_0-9]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(pqb200_[A-Za-z_0-9]+)\s*\(", text)))
 
 
 def test_header_symbols_are_exported_and_bound():
