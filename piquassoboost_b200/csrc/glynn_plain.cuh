@@ -19,7 +19,7 @@
 //   * per step: 2N DADD/DFMA (column update) + 4(N-1) DMUL/DFMA (complex product chains; the last
 //     complex multiply is fused into the accumulator) = 6N-4 FP64 instructions for 8N algorithmic
 //     flops;
-//   * every 2 terms the partial sum is folded into a double-double accumulator (TwoSum), chunk sums
+//   * every DDP (default 8) terms the partial sum is folded into a double-double accumulator (TwoSum), chunk sums
 //     are combined per thread in dd, then warp shuffle -> shared -> one partial per CTA -> the last
 //     CTA reduces all partials in a fixed order (deterministic) into 4 doubles (re.hi re.lo im.hi
 //     im.lo);
@@ -150,7 +150,9 @@ __device__ __forceinline__ void cmul(double& xr, double& xi, double yr, double y
 }
 
 // One Gray term: acc += (NEG ? -1 : +1) * prod_j c[j], with CH independent multiply chains for ILP.
-template <int N, bool NEG>
+constexpr int default_chains(int n) { return (n >= 16) ? 4 : (n >= 4 ? 2 : 1); }
+
+template <int N, bool NEG, int CH = default_chains(N)>
 __device__ __forceinline__ void term_acc(const double (&cr)[N], const double (&ci)[N],
                                          double& acc_re, double& acc_im) {
     if (N == 1) {
@@ -158,7 +160,6 @@ __device__ __forceinline__ void term_acc(const double (&cr)[N], const double (&c
         acc_im += NEG ? -ci[0] : ci[0];
         return;
     }
-    constexpr int CH = (N >= 16) ? 4 : (N >= 4 ? 2 : 1);
     double qr[CH], qi[CH];
 #pragma unroll
     for (int k = 0; k < CH; k++) {
@@ -168,12 +169,11 @@ __device__ __forceinline__ void term_acc(const double (&cr)[N], const double (&c
     // one factor is left out of the chains so that the last multiply can be fused into the accumulate
 #pragma unroll
     for (int j = CH; j < N - 1; j++) cmul(qr[j % CH], qi[j % CH], cr[j], ci[j]);
-    if (CH == 4) {
-        cmul(qr[0], qi[0], qr[1], qi[1]);
-        cmul(qr[2], qi[2], qr[3], qi[3]);
-        cmul(qr[0], qi[0], qr[2], qi[2]);
-    } else if (CH == 2) {
-        cmul(qr[0], qi[0], qr[1], qi[1]);
+    // combine the chains pairwise
+#pragma unroll
+    for (int w = 1; w < CH; w *= 2) {
+#pragma unroll
+        for (int k = 0; k + w < CH; k += 2 * w) cmul(qr[k], qi[k], qr[k + w], qi[k + w]);
     }
     cmul_acc<NEG>(acc_re, acc_im, qr[0], qi[0], cr[N - 1], ci[N - 1]);
 }
@@ -189,7 +189,9 @@ __device__ __forceinline__ void toggle_row(const PlainParams<N>& p, int row, dou
     }
 }
 
-template <int N>
+// DDP: the partial sum is folded into the double-double accumulator every DDP terms (a power of two
+// >= 2); CH: independent multiply chains per term.
+template <int N, int DDP = 8, int CH = default_chains(N)>
 __global__ void __launch_bounds__(kPlainThreads, 1)
 glynn_plain_kernel(const __grid_constant__ PlainParams<N> p) {
     const int rows = p.rows;
@@ -217,16 +219,20 @@ glynn_plain_kernel(const __grid_constant__ PlainParams<N> p) {
         }
         cdd cacc = cdd_zero();
         const unsigned int g0lo = (unsigned int)g0;
+        double bs_re = 0.0, bs_im = 0.0;
 #pragma unroll 1
         for (unsigned int s = 0; s < nsteps; s += 2) {
             // two consecutive terms g, g+1 (g = g0+s even): Gray bit 0 is set going into g+1 iff bit 1
             // of g is clear (warp-uniform whenever L >= 2)
-            double bs_re = 0.0, bs_im = 0.0;
-            term_acc<N, false>(cr, ci, bs_re, bs_im);
+            term_acc<N, false, CH>(cr, ci, bs_re, bs_im);
             toggle_row<N>(p, rows - 1, (((g0lo | s) >> 1) & 1u) ? 1.0 : -1.0, cr, ci);
-            term_acc<N, true>(cr, ci, bs_re, bs_im);
-            dd_add_d(cacc.re, bs_re);
-            dd_add_d(cacc.im, bs_im);
+            term_acc<N, true, CH>(cr, ci, bs_re, bs_im);
+            if (DDP == 2 || (s & (DDP - 2)) == (DDP - 2)) {
+                dd_add_d(cacc.re, bs_re);
+                dd_add_d(cacc.im, bs_im);
+                bs_re = 0.0;
+                bs_im = 0.0;
+            }
             // ---- general toggle into term g+2: Gray bit b = ctz(s+2) >= 1, warp-uniform row, per-thread
             // sign (it depends on the chunk index only for b == L-1).  Unconditional so that the loop
             // body is one basic block: after the last pair b == L and row rows-1-L >= 0 is toggled
