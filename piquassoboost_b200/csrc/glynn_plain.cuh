@@ -150,7 +150,11 @@ __device__ __forceinline__ void cmul(double& xr, double& xi, double yr, double y
 }
 
 // One Gray term: acc += (NEG ? -1 : +1) * prod_j c[j], with CH independent multiply chains for ILP.
-constexpr int default_chains(int n) { return (n >= 16) ? 4 : (n >= 4 ? 2 : 1); }
+// multiply chains per term, tuned on B200 (tools/microbench/mb2.cu, profiles/mb2_r1.log): long products
+// want few chains (register pressure at N >= 36), short ones want many (latency)
+constexpr int default_chains(int n) {
+    return n >= 36 ? 2 : n >= 26 ? 4 : n >= 18 ? 8 : n >= 8 ? 4 : n >= 4 ? 2 : 1;
+}
 
 template <int N, bool NEG, int CH = default_chains(N)>
 __device__ __forceinline__ void term_acc(const double (&cr)[N], const double (&ci)[N],
