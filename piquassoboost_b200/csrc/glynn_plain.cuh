@@ -247,6 +247,10 @@ glynn_plain_kernel(const __grid_constant__ PlainParams<N> p) {
             const double sg = (((g >> b) ^ (g >> (b + 1))) & 1ull) ? -1.0 : 1.0;
             toggle_row<N>(p, rows - 1 - b, sg, cr, ci);
         }
+        if (DDP > 2) {  // leftover when the chunk is shorter than DDP terms (bs is zero otherwise)
+            dd_add_d(cacc.re, bs_re);
+            dd_add_d(cacc.im, bs_im);
+        }
         // every group of terms starts with the parity of the chunk's start code
         if (__popcll(gray0) & 1) {
             cacc.re = dd_neg(cacc.re);

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -214,6 +215,10 @@ PlainPlan plan_plain(int rows, int cols, int max_resident_threads, unsigned long
             best = cost;
             pl.L = L;
         }
+    }
+    if (const char* f = getenv("PQB200_FORCE_L")) {  // tuning / debugging aid
+        const int L = atoi(f);
+        if (L >= 1 && L <= rows - 1) pl.L = L;
     }
     pl.nchunks = 1ull << (rows - 1 - pl.L);
     return pl;
