@@ -158,7 +158,6 @@ def run_b200(args, rank, local_rank, world):
     n = args.n
     A_host = torch.from_numpy(haar(n)).pin_memory()        # the step's input lives in pinned host memory
     A_np = A_host.numpy()
-    a_ptr = ctypes.cast(A_host.data_ptr(), _lib.c_double_p)
     partial = torch.zeros(4, dtype=torch.float64, device=dev)
     gathered = torch.zeros(4 * world, dtype=torch.float64, device=dev)
     # a real (non-default) stream: its handle is passed to the C ABI so that the kernel, the NCCL
@@ -166,20 +165,17 @@ def run_b200(args, rank, local_rank, world):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
 
+    from piquassoboost_b200.distributed import combine_partials, gpu_shard_fn
+
     def step():
-        _lib.check(lib.pqb200_permanent_shard(a_ptr, n, n, n, local_rank, rank, world, None,
-                                              ctypes.c_void_p(partial.data_ptr()),
-                                              ctypes.c_void_p(stream.cuda_stream)))
+        gpu_shard_fn(A_np, rank, world, local_rank, d_out=partial.data_ptr(), stream=stream.cuda_stream)
         if world > 1:
             dist.all_gather_into_tensor(gathered, partial)
         else:
             gathered.copy_(partial)
 
     def result():
-        parts = gathered.cpu().numpy()
-        out = np.zeros(2)
-        _lib.check(lib.pqb200_permanent_combine(_lib.dptr(parts), world, n, _lib.dptr(out)))
-        return complex(out[0], out[1])
+        return combine_partials(gathered.cpu().numpy(), n)
 
     def barrier():
         if world > 1:
@@ -210,9 +206,7 @@ def run_b200(args, rank, local_rank, world):
     kreps = max(1, min(args.steps, 3))
     k0.record()
     for _ in range(kreps):
-        _lib.check(lib.pqb200_permanent_shard(a_ptr, n, n, n, local_rank, rank, world, None,
-                                              ctypes.c_void_p(partial.data_ptr()),
-                                              ctypes.c_void_p(stream.cuda_stream)))
+        gpu_shard_fn(A_np, rank, world, local_rank, d_out=partial.data_ptr(), stream=stream.cuda_stream)
     k1.record()
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / kreps

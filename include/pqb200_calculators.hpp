@@ -1,0 +1,114 @@
+// pqb200_calculators.hpp -- C++ calculator classes with the reference's names and call signatures,
+// forwarding to the C ABI (include/pqb200.h).  This is the shim a piquassoboost maintainer drops in
+// place of the TBB bodies: each class keeps `calculate(...) -> Complex16` and the reference's error
+// convention (`throw std::string`).  It is templated on the container types so that it compiles both
+// against the reference's own `pic::matrix` / `pic::PicState_int64`
+// (common/source/matrix_base.hpp:41-561: members rows, cols, stride, get_data();
+//  common/source/PicState_base.hpp:34-226: size(), get_data()) and against any struct with the same
+// members (tests/cpp/shim_smoke.cpp).
+//
+//   reference class / method                                      file:line (piquassoboost/...)
+//   BBFGPermanentCalculator::calculate(mtx, use_extended, use_inf) sampling/source/BBFGPermanentCalculator.cpp:89-126
+//   GlynnPermanentCalculator<M,P>::calculate(mtx)                  sampling/source/GlynnPermanentCalculator.hpp:47-57
+//   GlynnPermanentCalculatorSimple<M,P>::calculate(mtx)            sampling/source/GlynnPermanentCalculatorSimple.hpp:47-53
+//   BBFGPermanentCalculatorRepeated::calculate(mtx, col, row, ..)  sampling/source/BBFGPermanentCalculatorRepeated.cpp:74-141
+//   GlynnPermanentCalculatorRepeated<M,P>::calculate(mtx, in, out) sampling/source/GlynnPermanentCalculatorRepeated.hpp:49-74
+//   compute_pmf(U, sample, current_input)                          sampling/simulation_strategies/source/samplingHelperFunctions.cpp:78-342
+#pragma once
+#include <complex>
+#include <string>
+#include <vector>
+
+#include "pqb200.h"
+
+namespace pqb200 {
+
+using Complex16 = std::complex<double>;
+
+inline void check(int rc) {
+    if (rc != PQB200_OK) throw std::string(pqb200_last_error());
+}
+
+/// number of GPUs a single calculate() is sharded over (0 = all)
+inline int& default_ndev() {
+    static int n = 0;
+    return n;
+}
+
+class BBFGPermanentCalculator {
+public:
+    template <class Matrix>
+    Complex16 calculate(Matrix& mtx, bool use_extended = false, bool use_inf = false) {
+        (void)use_extended;  // one numeric mode serves double and long double requests
+        if (use_inf) throw std::string("MPFR Not included");  // BBFGPermanentCalculator.cpp:100-107
+        double out[2];
+        check(pqb200_permanent(reinterpret_cast<const double*>(mtx.get_data()), mtx.rows, mtx.cols,
+                               mtx.stride, default_ndev(), out));
+        return Complex16(out[0], out[1]);
+    }
+};
+
+class GlynnPermanentCalculator {
+public:
+    template <class Matrix>
+    Complex16 calculate(Matrix& mtx) {
+        return BBFGPermanentCalculator().calculate(mtx);
+    }
+};
+using GlynnPermanentCalculatorDouble = GlynnPermanentCalculator;
+using GlynnPermanentCalculatorLongDouble = GlynnPermanentCalculator;
+
+class GlynnPermanentCalculatorSimple {
+public:
+    template <class Matrix>
+    Complex16 calculate(Matrix& mtx) {
+        if (mtx.rows != mtx.cols) return Complex16(0.0, 0.0);  // GlynnPermanentCalculatorSimple.hpp:67-70
+        return BBFGPermanentCalculator().calculate(mtx);
+    }
+};
+
+class BBFGPermanentCalculatorRepeated {
+public:
+    /// col_mult = input state, row_mult = output state (reference argument order)
+    template <class Matrix, class State>
+    Complex16 calculate(Matrix& mtx, State& col_mult, State& row_mult, bool use_extended = false,
+                        bool use_inf = false) {
+        (void)use_extended;
+        if (use_inf) throw std::string("MPFR Not included");
+        std::vector<int64_t> c(col_mult.size()), r(row_mult.size());
+        for (size_t i = 0; i < c.size(); i++) c[i] = (int64_t)col_mult[i];
+        for (size_t i = 0; i < r.size(); i++) r[i] = (int64_t)row_mult[i];
+        double out[2];
+        check(pqb200_permanent_repeated(reinterpret_cast<const double*>(mtx.get_data()), mtx.rows,
+                                        mtx.cols, mtx.stride, r.data(), c.data(), default_ndev(), out));
+        return Complex16(out[0], out[1]);
+    }
+};
+
+class GlynnPermanentCalculatorRepeated {
+public:
+    template <class Matrix, class State>
+    Complex16 calculate(Matrix& mtx, State& input_state, State& output_state) {
+        return BBFGPermanentCalculatorRepeated().calculate(mtx, input_state, output_state);
+    }
+};
+using GlynnPermanentCalculatorRepeatedDouble = GlynnPermanentCalculatorRepeated;
+using GlynnPermanentCalculatorRepeatedLongDouble = GlynnPermanentCalculatorRepeated;
+
+/// compute_pmf for one shot; returns m probabilities
+template <class Matrix, class State>
+std::vector<double> compute_pmf(Matrix& interferometer_matrix, State& sample, State& current_input) {
+    const size_t m = interferometer_matrix.rows;
+    std::vector<int64_t> s(m), c(m);
+    for (size_t i = 0; i < m; i++) {
+        s[i] = (int64_t)sample[i];
+        c[i] = (int64_t)current_input[i];
+    }
+    std::vector<double> pmf(m);
+    check(pqb200_pmf_layer(reinterpret_cast<const double*>(interferometer_matrix.get_data()), m,
+                           interferometer_matrix.stride, s.data(), c.data(), 1, default_ndev(),
+                           pmf.data()));
+    return pmf;
+}
+
+}  // namespace pqb200

@@ -1,0 +1,64 @@
+"""One-process-per-GPU evaluation of a single permanent: every rank computes its shard of the Gray
+index space (pqb200_permanent_shard), the 4-double partials are all-gathered with
+torch.distributed (NCCL on GPUs; gloo in the CPU tests) and folded in rank order with
+double-double adds (pqb200_permanent_combine).  torch is plumbing only: the compute is the C ABI.
+
+The reference has no counterpart for splitting ONE permanent (its optional MPI mode shards shots,
+CGeneralizedCliffordsBSimulationStrategy.cpp:158-231); the partition mirrors what its TBB chunking
+does inside one process (BBFGPermanentCalculator.hpp:120-134).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+def combine_partials(parts, rows):
+    """Fold `len(parts)//4` partials (re.hi re.lo im.hi im.lo each), apply 2^-(rows-1)."""
+    parts = np.ascontiguousarray(parts, dtype=np.float64).reshape(-1)
+    out = np.zeros(2)
+    _lib.check(_lib.load().pqb200_permanent_combine(_lib.dptr(parts), parts.size // 4, rows,
+                                                    _lib.dptr(out)))
+    return complex(out[0], out[1])
+
+
+def gpu_shard_fn(a, rank, world, device, d_out=None, stream=None):
+    """This rank's partial on CUDA device `device`.  With d_out (a device pointer) the 4 doubles stay
+    on the device and nothing synchronises; otherwise they are returned as a numpy array."""
+    a = _lib.as_matrix(a)
+    n, m = a.shape
+    host = None if d_out is not None else np.zeros(4)
+    _lib.check(_lib.load().pqb200_permanent_shard(
+        _lib.dptr(a), n, m, a.strides[0] // 16, device, rank, world,
+        None if host is None else _lib.dptr(host),
+        None if d_out is None else ctypes.c_void_p(d_out),
+        None if stream is None else ctypes.c_void_p(stream)))
+    return host
+
+
+def permanent_distributed(a, group=None, device=None, shard_fn=None):
+    """perm(a), computed cooperatively by all ranks of `group`; every rank returns the value.
+
+    shard_fn(a, rank, world) -> 4 doubles lets the tests substitute the per-rank compute; the default
+    is the CUDA engine on `device` (default: the current torch CUDA device)."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    a = _lib.as_matrix(a)
+    backend = dist.get_backend(group)
+    if shard_fn is None:
+        if device is None:
+            device = torch.cuda.current_device()
+        dev = torch.device("cuda", device)
+        partial = torch.zeros(4, dtype=torch.float64, device=dev)
+        gathered = torch.zeros(4 * world, dtype=torch.float64, device=dev)
+        gpu_shard_fn(a, rank, world, device, d_out=partial.data_ptr(),
+                     stream=torch.cuda.current_stream(dev).cuda_stream or None)
+    else:
+        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        partial = torch.as_tensor(np.asarray(shard_fn(a, rank, world), dtype=np.float64)).to(dev)
+        gathered = torch.zeros(4 * world, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(gathered, partial, group=group)
+    return combine_partials(gathered.cpu().numpy(), a.shape[0])

@@ -117,3 +117,18 @@ def test_errors_are_raised_not_swallowed(pqb):
         pqb.GlynnPermanentCalculator_wrapper(np.eye(3), 3).calculate()    # DFE id
     with pytest.raises(Exception):
         pqb.GlynnPermanentInf(np.eye(3)).calculate()                      # MPFR id
+
+
+@pytest.mark.parametrize("L", [1, 2, 3, 4, 5, 7, 9])
+def test_every_chunk_length_gives_the_same_value(pqb, ref, L):
+    """The chunk length only changes the order of summation (and exercises the short-chunk paths of
+    the kernel: chunks shorter than the double-double fold period, the last-pair dummy toggle)."""
+    import os
+    A = haar_unitary(11, 1234)
+    want = ref.bbfg(A, True)
+    os.environ["PQB200_FORCE_L"] = str(L)
+    try:
+        got = pqb.GlynnPermanent(A).calculate()
+    finally:
+        del os.environ["PQB200_FORCE_L"]
+    assert relerr(got, want) < TOL, (L, got, want)
