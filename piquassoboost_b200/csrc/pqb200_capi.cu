@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <random>
 #include <string>
@@ -83,6 +84,16 @@ rep_launch_fn g_rep_launch[kPlainTableSize];
 
 thread_local std::string g_err;
 thread_local pqb200_stats g_stats = {0.0, 0.0, 0, 0};
+
+// PQB200_TRACE=1: host-side phase timings of the batch paths on stderr (tuning aid)
+bool trace_on() {
+    static int on = -1;
+    if (on < 0) on = getenv("PQB200_TRACE") ? 1 : 0;
+    return on == 1;
+}
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -579,17 +590,19 @@ static int run_batch_on_device(DeviceCtx& c, const std::vector<BatchItem>& items
     int rc = grow(&c.b_out, &c.b_out_cap, 16 * std::max<size_t>(nslots, 1));
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(c.b_out, prefill.data(), 16 * nslots, cudaMemcpyHostToDevice, c.stream));
-    // group the kernel jobs by column bucket
-    std::vector<std::vector<BatchJobHost>> buckets(64);
+    // group the kernel jobs by column bucket (counting sort into one flat array)
+    size_t count[64] = {0}, start[64];
     for (const BatchItem& it : items)
-        if (it.kind == kJobKernel) buckets[(size_t)batch_bucket(it.job.N)].push_back(it.job);
-    std::vector<BatchJobHost> flat;
+        if (it.kind == kJobKernel) count[batch_bucket(it.job.N)]++;
+    size_t tot = 0;
+    for (int b = 0; b < 64; b++) { start[b] = tot; tot += count[b]; }
+    static thread_local std::vector<BatchJobHost> flat;
+    flat.resize(tot);
     std::vector<std::pair<int, std::pair<size_t, size_t>>> launches;  // bucket, (offset, count)
     for (int b = 0; b < 64; b++)
-        if (!buckets[b].empty()) {
-            launches.push_back({b, {flat.size(), buckets[b].size()}});
-            flat.insert(flat.end(), buckets[b].begin(), buckets[b].end());
-        }
+        if (count[b]) launches.push_back({b, {start[b], count[b]}});
+    for (const BatchItem& it : items)
+        if (it.kind == kJobKernel) flat[start[batch_bucket(it.job.N)]++] = it.job;
     if (flat.empty()) return PQB200_OK;
     rc = grow(&c.b_jobs, &c.b_jobs_cap, sizeof(BatchJobHost) * flat.size());
     if (rc) return rc;
@@ -762,44 +775,53 @@ int pqb200_permanent_batch(const double* const* a, const size_t* rows, const siz
 
 // pmf rows for shots [s0, s1) on device c; async on c.stream, results left in c.b_pmf
 static int pmf_layer_on_device(DeviceCtx& c, const double* u, size_t m, size_t stride,
-                               const int64_t* samples, const int64_t* inputs, size_t s0, size_t s1,
-                               std::vector<std::pair<size_t, std::vector<int64_t>>>& too_big) {
+                               const int64_t* samples, const int64_t* inputs, size_t s0, size_t s1) {
     const size_t S = s1 - s0;
-    std::vector<BatchItem> items;
-    std::vector<double> prefill(2 * S * m, 0.0), weight(S * m, 0.0);
+    const double t_begin = now_ms();
+    static thread_local std::vector<BatchItem> items;
+    static thread_local std::vector<double> prefill, weight;
+    items.clear();
+    prefill.assign(2 * S * m, 0.0);
+    weight.assign(S * m, 0.0);
     std::vector<int64_t> cols(m);
+    BatchSide rs, cs;
     for (size_t s = s0; s < s1; s++) {
         const int64_t* sample = samples + s * m;
         const int64_t* input = inputs + s * m;
+        analyze_side(m, sample, rs);  // the row side is shared by all sub-permanents of the shot
+        memcpy(cols.data(), input, m * sizeof(int64_t));
         for (size_t i = 0; i < m; i++) {
             if (input[i] <= 0) continue;
             weight[(s - s0) * m + i] = (double)input[i];
-            memcpy(cols.data(), input, m * sizeof(int64_t));
             cols[i]--;  // input_loc = current_input - e_i (samplingHelperFunctions.cpp:139-143)
-            BatchItem it;
+            analyze_side(m, cols.data(), cs);
+            items.emplace_back();
+            BatchItem& it = items.back();
             memset(&it.job, 0, sizeof(it.job));
-            std::string err;
-            int rc = make_batch_job(m, m, sample, cols.data(), it.job, it.kind, err);
+            const char* err = nullptr;
+            int rc = make_batch_job_sides(rs, cs, it.job, it.kind, &err);
             if (rc) return fail(rc, err);
             const size_t slot = (s - s0) * m + i;
             it.job.out_slot = (int)slot;
             it.job.ustride = (int)stride;
             it.job.uoff = 0;
-            if (it.kind == kJobTrivialOne) prefill[2 * slot] = 1.0;
-            else if (it.kind == kJobSingleRow) single_row_value(u, stride, it.job, &prefill[2 * slot]);
-            else if (it.kind == kJobTooBig) {
-                // grid-wide kernels, synchronously, before this device's batch is enqueued
-                double v[2];
-                rc = repeated_locked(u, m, m, stride, sample, cols.data(), 1, v);
-                if (rc) return rc;
-                prefill[2 * slot] = v[0];
-                prefill[2 * slot + 1] = v[1];
-            } else {
-                items.push_back(it);
+            if (it.kind != kJobKernel) {
+                if (it.kind == kJobTrivialOne) prefill[2 * slot] = 1.0;
+                else if (it.kind == kJobSingleRow) single_row_value(u, stride, it.job, &prefill[2 * slot]);
+                else {
+                    // Gray space too large for one CTA: grid-wide kernels, synchronously
+                    double v[2];
+                    rc = repeated_locked(u, m, m, stride, sample, cols.data(), 1, v);
+                    if (rc) return rc;
+                    prefill[2 * slot] = v[0];
+                    prefill[2 * slot + 1] = v[1];
+                }
+                items.pop_back();
             }
+            cols[i]++;
         }
     }
-    (void)too_big;
+    const double t_jobs = now_ms();
     CUDA_TRY(cudaSetDevice(c.dev));
     int rc = grow(&c.b_u, &c.b_u_cap, 16 * m * stride);
     if (rc) return rc;
@@ -814,6 +836,9 @@ static int pmf_layer_on_device(DeviceCtx& c, const double* u, size_t m, size_t s
     CUDA_TRY(pmf_combine_launch(c.b_u, (int)stride, (int)m, c.b_out, (const double*)c.b_weight,
                                 (double*)c.b_pmf, (int)S, c.stream));
     g_stats.launches += 1;
+    if (trace_on())
+        fprintf(stderr, "[pqb200] pmf layer dev %d: %zu shots, %zu kernel jobs; build %.2f ms, upload+launch %.2f ms\n",
+                c.dev, S, items.size(), t_jobs - t_begin, now_ms() - t_jobs);
     return PQB200_OK;
 }
 
@@ -821,12 +846,12 @@ static int pmf_layer_on_device(DeviceCtx& c, const double* u, size_t m, size_t s
 static int pmf_layer_locked(const double* u, size_t m, size_t stride, const int64_t* samples,
                             const int64_t* inputs, size_t S, int used, double* pmf) {
     used = (int)std::min<size_t>((size_t)used, S);
-    std::vector<std::pair<size_t, std::vector<int64_t>>> too_big;
+    const double t_layer = now_ms();
     CUDA_TRY(cudaSetDevice(g_devs[0].dev));
     CUDA_TRY(cudaEventRecord(g_devs[0].e0, g_devs[0].stream));
     for (int d = 0; d < used; d++) {
         const size_t s0 = S * (size_t)d / (size_t)used, s1 = S * (size_t)(d + 1) / (size_t)used;
-        int rc = pmf_layer_on_device(g_devs[d], u, m, stride, samples, inputs, s0, s1, too_big);
+        int rc = pmf_layer_on_device(g_devs[d], u, m, stride, samples, inputs, s0, s1);
         if (rc) return rc;
         if (d == 0) CUDA_TRY(cudaEventRecord(g_devs[0].e1, g_devs[0].stream));
     }
@@ -842,6 +867,7 @@ static int pmf_layer_locked(const double* u, size_t m, size_t stride, const int6
     CUDA_TRY(cudaEventElapsedTime(&ms, g_devs[0].e0, g_devs[0].e1));
     g_stats.kernel_ms += ms;
     g_stats.ndev = used;
+    if (trace_on()) fprintf(stderr, "[pqb200] pmf layer total %.2f ms (device-0 stream %.2f ms)\n", now_ms() - t_layer, ms);
     return PQB200_OK;
 }
 
