@@ -190,7 +190,7 @@ glynn_batch_kernel(const double2* __restrict__ Ubuf, const BatchJob* __restrict_
             term_prod<NMAX>(cr, ci, pr, pi);
             bs_re = fma(e.w, pr, bs_re);
             bs_im = fma(e.w, pi, bs_im);
-            if (t & 1u) {
+            if ((t & 7u) == 7u) {
                 dd_add_d(cacc.re, bs_re);
                 dd_add_d(cacc.im, bs_im);
                 bs_re = 0.0;

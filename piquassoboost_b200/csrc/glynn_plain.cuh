@@ -152,7 +152,7 @@ __device__ __forceinline__ void cmul(double& xr, double& xi, double yr, double y
 // One Gray term: acc += (NEG ? -1 : +1) * prod_j c[j], with CH independent multiply chains for ILP.
 // multiply chains per term, tuned on B200 (tools/microbench/mb2.cu, profiles/mb2_r1.log): long products
 // want few chains (register pressure at N >= 36), short ones want many (latency)
-constexpr int default_chains(int n) {
+__host__ __device__ constexpr int default_chains(int n) {
     return n >= 36 ? 2 : n >= 26 ? 4 : n >= 18 ? 8 : n >= 8 ? 4 : n >= 4 ? 2 : 1;
 }
 

@@ -66,7 +66,7 @@ struct RepParams {
 template <int N>
 __device__ __forceinline__ void term_prod(const double (&cr)[N], const double (&ci)[N], double& pr,
                                           double& pi) {
-    constexpr int CH = (N >= 16) ? 4 : (N >= 4 ? 2 : 1);
+    constexpr int CH = default_chains(N) <= N ? default_chains(N) : 1;
     double qr[CH], qi[CH];
 #pragma unroll
     for (int k = 0; k < CH; k++) {
@@ -75,12 +75,10 @@ __device__ __forceinline__ void term_prod(const double (&cr)[N], const double (&
     }
 #pragma unroll
     for (int j = CH; j < N; j++) cmul(qr[j % CH], qi[j % CH], cr[j], ci[j]);
-    if (CH == 4) {
-        cmul(qr[0], qi[0], qr[1], qi[1]);
-        cmul(qr[2], qi[2], qr[3], qi[3]);
-        cmul(qr[0], qi[0], qr[2], qi[2]);
-    } else if (CH == 2) {
-        cmul(qr[0], qi[0], qr[1], qi[1]);
+#pragma unroll
+    for (int w = 1; w < CH; w *= 2) {
+#pragma unroll
+        for (int k = 0; k + w < CH; k += 2 * w) cmul(qr[k], qi[k], qr[k + w], qi[k + w]);
     }
     pr = qr[0];
     pi = qi[0];
@@ -111,11 +109,9 @@ glynn_repeated_kernel(const __grid_constant__ RepParams<N> p) {
         // ---- decode the high digits (most significant first), build their reflected Gray values,
         //      the high part of the column sums, the binomial weight and the parity
         //      (n_aryGrayCodeCounter::initialize, n_aryGrayCodeCounter.cpp:114-140)
+        // pass 1 (integers only): parity of the high Gray digits, their binomial weight, sum of k
         int par = 0, ksum = 0;
         double whigh = 1.0;
-        double hr[N], hi[N];
-#pragma unroll
-        for (int j = 0; j < N; j++) hr[j] = hi[j] = 0.0;
 #pragma unroll 1
         for (int d = D - 1; d >= q; d--) {
             const int radix = p.radix[d];
@@ -124,15 +120,24 @@ glynn_repeated_kernel(const __grid_constant__ RepParams<N> p) {
             par ^= k & 1;
             ksum += k;
             whigh *= p.binom[d * (kRepMaxN + 1) + k];
-            rep_toggle<N>(p, d + 1, 0.5 * (double)(radix - 1 - 2 * k), hr, hi);
         }
         const int P = par;
         double cr[N], ci[N];
 #pragma unroll
         for (int j = 0; j < N; j++) {
             const double2 b = p.base[P * N + j];
-            cr[j] = b.x + hr[j];
-            ci[j] = b.y + hi[j];
+            cr[j] = b.x;
+            ci[j] = b.y;
+        }
+        // pass 2: add the high rows, (r - 2k) * a = 0.5 (r - 2k) * (2a)
+        par = 0;
+#pragma unroll 1
+        for (int d = D - 1; d >= q; d--) {
+            const int radix = p.radix[d];
+            const int cnt = (int)((cc / p.weight[d]) % (unsigned long long)radix);
+            const int k = par ? radix - 1 - cnt : cnt;
+            par ^= k & 1;
+            rep_toggle<N>(p, d + 1, 0.5 * (double)(radix - 1 - 2 * k), cr, ci);
         }
         // ---- sweep the low digits
         cdd cacc = cdd_zero();
@@ -153,7 +158,7 @@ glynn_repeated_kernel(const __grid_constant__ RepParams<N> p) {
             term_prod<N>(cr, ci, pr, pi);
             bs_re = fma(e.w, pr, bs_re);
             bs_im = fma(e.w, pi, bs_im);
-            if (t & 1u) {
+            if ((t & 7u) == 7u) {  // fold into the double-double accumulator every 8 terms
                 dd_add_d(cacc.re, bs_re);
                 dd_add_d(cacc.im, bs_im);
                 bs_re = 0.0;

@@ -14,6 +14,7 @@
 #include <mutex>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pqb200.h"
@@ -602,7 +603,10 @@ static int run_batch_on_device(DeviceCtx& c, const std::vector<BatchItem>& items
     for (int b = 0; b < 64; b++)
         if (count[b]) launches.push_back({b, {start[b], count[b]}});
     for (const BatchItem& it : items)
-        if (it.kind == kJobKernel) flat[start[batch_bucket(it.job.N)]++] = it.job;
+        if (it.kind == kJobKernel) {
+            flat[start[batch_bucket(it.job.N)]++] = it.job;
+            g_stats.gray_steps += (double)it.job.len * (double)it.job.nchunks;
+        }
     if (flat.empty()) return PQB200_OK;
     rc = grow(&c.b_jobs, &c.b_jobs_cap, sizeof(BatchJobHost) * flat.size());
     if (rc) return rc;
@@ -783,42 +787,69 @@ static int pmf_layer_on_device(DeviceCtx& c, const double* u, size_t m, size_t s
     items.clear();
     prefill.assign(2 * S * m, 0.0);
     weight.assign(S * m, 0.0);
-    std::vector<int64_t> cols(m);
-    BatchSide rs, cs;
-    for (size_t s = s0; s < s1; s++) {
-        const int64_t* sample = samples + s * m;
-        const int64_t* input = inputs + s * m;
-        analyze_side(m, sample, rs);  // the row side is shared by all sub-permanents of the shot
-        memcpy(cols.data(), input, m * sizeof(int64_t));
-        for (size_t i = 0; i < m; i++) {
-            if (input[i] <= 0) continue;
-            weight[(s - s0) * m + i] = (double)input[i];
-            cols[i]--;  // input_loc = current_input - e_i (samplingHelperFunctions.cpp:139-143)
-            analyze_side(m, cols.data(), cs);
-            items.emplace_back();
-            BatchItem& it = items.back();
-            memset(&it.job, 0, sizeof(it.job));
-            const char* err = nullptr;
-            int rc = make_batch_job_sides(rs, cs, it.job, it.kind, &err);
-            if (rc) return fail(rc, err);
-            const size_t slot = (s - s0) * m + i;
-            it.job.out_slot = (int)slot;
-            it.job.ustride = (int)stride;
-            it.job.uoff = 0;
-            if (it.kind != kJobKernel) {
-                if (it.kind == kJobTrivialOne) prefill[2 * slot] = 1.0;
-                else if (it.kind == kJobSingleRow) single_row_value(u, stride, it.job, &prefill[2 * slot]);
-                else {
-                    // Gray space too large for one CTA: grid-wide kernels, synchronously
-                    double v[2];
-                    rc = repeated_locked(u, m, m, stride, sample, cols.data(), 1, v);
-                    if (rc) return rc;
-                    prefill[2 * slot] = v[0];
-                    prefill[2 * slot + 1] = v[1];
+    // job construction is pure index work on disjoint shots: spread it over a few host threads
+    struct TooBig { size_t shot, mode, slot; };
+    const int nthreads = (int)std::max<size_t>(1, std::min<size_t>({(size_t)8, (size_t)std::thread::hardware_concurrency(), S / 64}));
+    std::vector<std::vector<BatchItem>> t_items((size_t)nthreads);
+    std::vector<std::vector<TooBig>> t_big((size_t)nthreads);
+    std::vector<int> t_rc((size_t)nthreads, 0);
+    std::vector<const char*> t_err((size_t)nthreads, nullptr);
+    auto build = [&](int t) {
+        const size_t b0 = s0 + S * (size_t)t / (size_t)nthreads, b1 = s0 + S * (size_t)(t + 1) / (size_t)nthreads;
+        std::vector<int64_t> cols(m);
+        BatchSide rs, cs;
+        std::vector<BatchItem>& out = t_items[(size_t)t];
+        out.reserve((b1 - b0) * 24);
+        for (size_t s = b0; s < b1; s++) {
+            const int64_t* sample = samples + s * m;
+            const int64_t* input = inputs + s * m;
+            analyze_side(m, sample, rs);  // the row side is shared by all sub-permanents of the shot
+            memcpy(cols.data(), input, m * sizeof(int64_t));
+            for (size_t i = 0; i < m; i++) {
+                if (input[i] <= 0) continue;
+                const size_t slot = (s - s0) * m + i;
+                weight[slot] = (double)input[i];
+                cols[i]--;  // input_loc = current_input - e_i (samplingHelperFunctions.cpp:139-143)
+                analyze_side(m, cols.data(), cs);
+                cols[i]++;
+                BatchItem it;
+                memset(&it.job, 0, sizeof(it.job));
+                const char* err = nullptr;
+                const int rc = make_batch_job_sides(rs, cs, it.job, it.kind, &err);
+                if (rc) {
+                    t_rc[(size_t)t] = rc;
+                    t_err[(size_t)t] = err;
+                    return;
                 }
-                items.pop_back();
+                it.job.out_slot = (int)slot;
+                it.job.ustride = (int)stride;
+                it.job.uoff = 0;
+                if (it.kind == kJobKernel) out.push_back(it);
+                else if (it.kind == kJobTrivialOne) prefill[2 * slot] = 1.0;
+                else if (it.kind == kJobSingleRow) single_row_value(u, stride, it.job, &prefill[2 * slot]);
+                else t_big[(size_t)t].push_back({s, i, slot});
             }
-            cols[i]++;
+        }
+    };
+    if (nthreads == 1) {
+        build(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; t++) pool.emplace_back(build, t);
+        for (auto& th : pool) th.join();
+    }
+    for (int t = 0; t < nthreads; t++) {
+        if (t_rc[(size_t)t]) return fail(t_rc[(size_t)t], t_err[(size_t)t]);
+        items.insert(items.end(), t_items[(size_t)t].begin(), t_items[(size_t)t].end());
+        for (const TooBig& tb : t_big[(size_t)t]) {
+            // Gray space too large for one CTA: grid-wide kernels, synchronously
+            std::vector<int64_t> cols(inputs + tb.shot * m, inputs + (tb.shot + 1) * m);
+            cols[tb.mode]--;
+            double v[2];
+            const int rc = repeated_locked(u, m, m, stride, samples + tb.shot * m, cols.data(), 1, v);
+            if (rc) return rc;
+            prefill[2 * tb.slot] = v[0];
+            prefill[2 * tb.slot + 1] = v[1];
         }
     }
     const double t_jobs = now_ms();
