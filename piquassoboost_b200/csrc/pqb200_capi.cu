@@ -794,7 +794,10 @@ static int pmf_layer_on_device(DeviceCtx& c, const double* u, size_t m, size_t s
     std::vector<std::vector<TooBig>> t_big((size_t)nthreads);
     std::vector<int> t_rc((size_t)nthreads, 0);
     std::vector<const char*> t_err((size_t)nthreads, nullptr);
-    auto build = [&](int t) {
+    // NB: `prefill` / `weight` are thread_local; worker threads must go through these pointers
+    double* const prefill_p = prefill.data();
+    double* const weight_p = weight.data();
+    auto build = [&, prefill_p, weight_p](int t) {
         const size_t b0 = s0 + S * (size_t)t / (size_t)nthreads, b1 = s0 + S * (size_t)(t + 1) / (size_t)nthreads;
         std::vector<int64_t> cols(m);
         BatchSide rs, cs;
@@ -808,7 +811,7 @@ static int pmf_layer_on_device(DeviceCtx& c, const double* u, size_t m, size_t s
             for (size_t i = 0; i < m; i++) {
                 if (input[i] <= 0) continue;
                 const size_t slot = (s - s0) * m + i;
-                weight[slot] = (double)input[i];
+                weight_p[slot] = (double)input[i];
                 cols[i]--;  // input_loc = current_input - e_i (samplingHelperFunctions.cpp:139-143)
                 analyze_side(m, cols.data(), cs);
                 cols[i]++;
@@ -825,8 +828,8 @@ static int pmf_layer_on_device(DeviceCtx& c, const double* u, size_t m, size_t s
                 it.job.ustride = (int)stride;
                 it.job.uoff = 0;
                 if (it.kind == kJobKernel) out.push_back(it);
-                else if (it.kind == kJobTrivialOne) prefill[2 * slot] = 1.0;
-                else if (it.kind == kJobSingleRow) single_row_value(u, stride, it.job, &prefill[2 * slot]);
+                else if (it.kind == kJobTrivialOne) prefill_p[2 * slot] = 1.0;
+                else if (it.kind == kJobSingleRow) single_row_value(u, stride, it.job, &prefill_p[2 * slot]);
                 else t_big[(size_t)t].push_back({s, i, slot});
             }
         }

@@ -82,3 +82,13 @@ def test_repeated_batch_many_states(pqb, ref):
         for j, b in enumerate(outs):
             want = ref.bbfg_repeated(U, a, b, True)
             assert abs(res[i][j] - want) <= 1e-11 * max(abs(want), 1e-12), (i, j)
+
+
+def test_many_shots_exercise_the_threaded_host_path(pqb, ref):
+    """>= 128 shots switch the host-side job construction to several threads; the shots must still
+    be exactly the reference's."""
+    U = haar_unitary(8, 31)
+    inp = np.array([1, 1, 1, 0, 1, 0, 1, 0], dtype=np.int64)
+    want = ref.simulate_B(U, 5, inp, 300)
+    got = np.array(pqb.GeneralizedCliffordsBSimulationStrategy(U, seed=5).simulate(inp, 300))
+    assert (got == want).all()
