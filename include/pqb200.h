@@ -95,19 +95,68 @@ int pqb200_permanent_repeated_batch(const double* a, size_t rows, size_t cols, s
 /* One photon step of the Clifford-Clifford B sampler for S shots at once.  For shot s:
  *   pmf[s][m'] ~ | sum_i input[s][i] * perm(U[sample[s] rows, (input[s]-e_i) cols]) * U[m'][i] |^2
  * normalised to sum 1.  Replaces compute_pmf (sampling/simulation_strategies/source/
- * samplingHelperFunctions.cpp:78-342) called once per shot. */
+ * samplingHelperFunctions.cpp:78-342) called once per shot.  Every shot must satisfy
+ * sum(input) == sum(sample) + 1 (else PQB200_ERR_MISMATCH, as the reference's calculator throws). */
 int pqb200_pmf_layer(const double* u, size_t m, size_t stride, const int64_t* samples /* S x m */,
                      const int64_t* inputs /* S x m */, size_t S, int ndev, double* pmf /* S x m */);
 
+/* The same layer computed as compute_pmf itself does it: one batched kernel job per sub-permanent
+ * (k repeated permanents per shot).  pqb200_pmf_layer evaluates all k of them in ONE Gray sweep
+ * (Laplace expansion, piquasso-module/src/permanent_laplace.cpp:43-233); this entry point is kept as
+ * its cross-check and serves shots with more than 40 photons. */
+int pqb200_pmf_layer_batched(const double* u, size_t m, size_t stride, const int64_t* samples,
+                             const int64_t* inputs, size_t S, int ndev, double* pmf);
+
+/* Seed the library's process-global std::mt19937.  Replaces seed_random_generator
+ * (samplingHelperFunctions.cpp:60-62), which every strategy's seed() forwards to. */
+int pqb200_seed(uint64_t seed);
+
+/* fill_r_sample for `shots` shots at once, the photon loop shared by the three B strategies
+ * (CGeneralizedCliffordsBSimulationStrategy.cpp:282-316): shot s inserts nphot[s] photons, the k-th
+ * one into input mode insert_modes[s*nmax+k] (update_input_by_single_photon with its random choice
+ * already resolved), computes the pmf layer and picks the output mode with the uniform draw
+ * draws[s*nmax+k] exactly as sample_from_pmf does (samplingHelperFunctions.cpp:350-374).  One kernel
+ * launch per device; one CTA per shot runs all of its photon steps.  nmax <= 40.
+ * samples_out: shots x m. */
+int pqb200_fill_r_samples(const double* u, size_t m, size_t stride, size_t shots, size_t nmax,
+                          const int32_t* nphot, const uint8_t* insert_modes, const double* draws,
+                          int ndev, int64_t* samples_out);
+
 /* The lossless Clifford-Clifford "B" sampler: `shots` samples of the output occupation for the
- * input occupation `input_state` behind interferometer U (m x m).  All shots advance through photon
- * step k together (one pqb200_pmf_layer per step); the std::mt19937 stream is consumed in exactly the
- * reference's order, so seeded runs reproduce the reference's shots.  Replaces
- *   CGeneralizedCliffordsBSimulationStrategy::seed + simulate
- *     sampling/simulation_strategies/source/CGeneralizedCliffordsBSimulationStrategy.cpp:113-116,137-316
- * samples_out: shots x m, in the reference's C++ generation order. */
+ * input occupation `input_state` behind interferometer U (m x m).  The global generator is consumed
+ * in exactly the reference's order (two draws per photon step, shot after shot), so seeded runs
+ * reproduce the reference's shots.  Replaces
+ *   CGeneralizedCliffordsBSimulationStrategy::simulate
+ *     sampling/simulation_strategies/source/CGeneralizedCliffordsBSimulationStrategy.cpp:137-316
+ * samples_out: shots x m, in the reference's C++ generation order.
+ * pqb200_simulate_B = pqb200_seed(seed) followed by pqb200_simulate_B_next;
+ * pqb200_simulate_B_next continues the generator (a second simulate() on the same strategy). */
 int pqb200_simulate_B(const double* u, size_t m, size_t stride, const int64_t* input_state,
                       size_t shots, uint64_t seed, int ndev, int64_t* samples_out);
+int pqb200_simulate_B_next(const double* u, size_t m, size_t stride, const int64_t* input_state,
+                           size_t shots, int ndev, int64_t* samples_out);
+
+/* Uniform-loss B sampler: per shot the surviving photon number is drawn from
+ * Binomial(n, transmittance^2) with one uniform draw, then that many photon steps follow.  Replaces
+ *   CGeneralizedCliffordsBUniformLossesSimulationStrategy::simulate
+ *     .../CGeneralizedCliffordsBUniformLossesSimulationStrategy.cpp:110-327
+ * Continues the global generator (call pqb200_seed first for a seeded run). */
+int pqb200_simulate_B_uniform_losses(const double* u, size_t m, size_t stride,
+                                     const int64_t* input_state, size_t shots, double transmittance,
+                                     int ndev, int64_t* samples_out);
+
+/* Lossy B sampler.  The uniform part of the losses is extracted from the interferometer first
+ * (uniform_loss = 1 - sigma_max^2, U <- U / sigma_max: `u` is UPDATED IN PLACE as the reference
+ * updates its member matrix, *uniform_loss_out receives the loss); per shot the photons of the
+ * first `approximated_modes` modes are put into one random approximated mode and thinned, the
+ * other modes are thinned binomially, then the photon loop runs.  shots == 0 only extracts the
+ * losses (no device needed).  Replaces
+ *   CGeneralizedCliffordsBLossySimulationStrategy::simulate
+ *     .../CGeneralizedCliffordsBLossySimulationStrategy.cpp:146-508
+ * Continues the global generator. */
+int pqb200_simulate_B_lossy(double* u, size_t m, size_t stride, const int64_t* input_state,
+                            size_t shots, int approximated_modes, int ndev,
+                            double* uniform_loss_out, int64_t* samples_out);
 
 /* Timing of the most recent compute call on this thread (CUDA events around the kernels on device
  * 0 of the call): kernel milliseconds, Gray steps executed, kernels launched. */

@@ -16,6 +16,9 @@
 //   sampling/source/BatchedPermanentCalculator.cpp:367-451        adaptInterferometer{,GlynnMultiplied}
 //   sampling/simulation_strategies/source/samplingHelperFunctions.cpp:78-342   compute_pmf
 //   sampling/simulation_strategies/source/CGeneralizedCliffordsBSimulationStrategy.cpp:137-278  simulate
+//   sampling/simulation_strategies/source/CGeneralizedCliffordsBUniformLossesSimulationStrategy.cpp:110-251  simulate
+//   sampling/simulation_strategies/source/CGeneralizedCliffordsBLossySimulationStrategy.cpp:146-330  simulate
+//     (its cblas_zgemm / LAPACKE_zgesvd come from blas_shim.cpp: BLAS/LAPACK are not in this image)
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -26,7 +29,9 @@
 #include "BBFGPermanentCalculatorRepeated.h"
 #include "BatchedPermanentCalculator.h"
 #include "CChinHuhPermanentCalculator.h"
+#include "CGeneralizedCliffordsBLossySimulationStrategy.h"
 #include "CGeneralizedCliffordsBSimulationStrategy.h"
+#include "CGeneralizedCliffordsBUniformLossesSimulationStrategy.h"
 #include "GlynnPermanentCalculator.h"
 #include "GlynnPermanentCalculatorRepeated.h"
 #include "GlynnPermanentCalculatorSimple.h"
@@ -220,6 +225,50 @@ int ref_simulate_B(const double* u, size_t m, uint64_t seed, const int64_t* inpu
     return guarded([&] {
         pic::matrix U = wrap_matrix(u, m, m);
         pic::CGeneralizedCliffordsBSimulationStrategy strategy(U, 0);
+        strategy.seed(seed);
+        pic::PicState_int64 in = make_state(input_state, m);
+        std::vector<pic::PicState_int64> samples = strategy.simulate(in, shots);
+        for (size_t k = 0; k < samples.size(); k++)
+            for (size_t i = 0; i < m; i++) samples_out[k * m + i] = samples[k][i];
+    });
+}
+
+// continues the reference's global generator (no reseed): a second simulate() of one strategy
+int ref_simulate_B_two_calls(const double* u, size_t m, uint64_t seed, const int64_t* input_state,
+                             int shots1, int shots2, int64_t* samples_out) {
+    return guarded([&] {
+        pic::matrix U = wrap_matrix(u, m, m);
+        pic::CGeneralizedCliffordsBSimulationStrategy strategy(U, 0);
+        strategy.seed(seed);
+        pic::PicState_int64 in = make_state(input_state, m);
+        size_t k = 0;
+        for (int shots : {shots1, shots2}) {
+            std::vector<pic::PicState_int64> samples = strategy.simulate(in, shots);
+            for (size_t j = 0; j < samples.size(); j++, k++)
+                for (size_t i = 0; i < m; i++) samples_out[k * m + i] = samples[j][i];
+        }
+    });
+}
+
+int ref_simulate_B_uniform_losses(const double* u, size_t m, uint64_t seed, const int64_t* input_state,
+                                  int shots, double transmittance, int64_t* samples_out) {
+    return guarded([&] {
+        pic::matrix U = wrap_matrix(u, m, m);
+        pic::CGeneralizedCliffordsBUniformLossesSimulationStrategy strategy(U, transmittance, 0);
+        strategy.seed(seed);
+        pic::PicState_int64 in = make_state(input_state, m);
+        std::vector<pic::PicState_int64> samples = strategy.simulate(in, shots);
+        for (size_t k = 0; k < samples.size(); k++)
+            for (size_t i = 0; i < m; i++) samples_out[k * m + i] = samples[k][i];
+    });
+}
+
+int ref_simulate_B_lossy(const double* u, size_t m, uint64_t seed, const int64_t* input_state, int shots,
+                         int approximated_modes, int64_t* samples_out) {
+    return guarded([&] {
+        std::vector<double> copy(u, u + 2 * m * m);  // a real zgesvd overwrites its input
+        pic::matrix U = wrap_matrix(copy.data(), m, m);
+        pic::CGeneralizedCliffordsBLossySimulationStrategy strategy(U, approximated_modes, 0);
         strategy.seed(seed);
         pic::PicState_int64 in = make_state(input_state, m);
         std::vector<pic::PicState_int64> samples = strategy.simulate(in, shots);

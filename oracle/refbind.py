@@ -41,6 +41,15 @@ def load():
         lib.ref_compute_pmf.argtypes = [_dp, ctypes.c_size_t, _ip, _ip, _dp]
         lib.ref_simulate_B.restype = ctypes.c_int
         lib.ref_simulate_B.argtypes = [_dp, ctypes.c_size_t, ctypes.c_uint64, _ip, ctypes.c_int, _ip]
+        lib.ref_simulate_B_two_calls.restype = ctypes.c_int
+        lib.ref_simulate_B_two_calls.argtypes = [_dp, ctypes.c_size_t, ctypes.c_uint64, _ip, ctypes.c_int,
+                                                 ctypes.c_int, _ip]
+        lib.ref_simulate_B_uniform_losses.restype = ctypes.c_int
+        lib.ref_simulate_B_uniform_losses.argtypes = [_dp, ctypes.c_size_t, ctypes.c_uint64, _ip, ctypes.c_int,
+                                                      ctypes.c_double, _ip]
+        lib.ref_simulate_B_lossy.restype = ctypes.c_int
+        lib.ref_simulate_B_lossy.argtypes = [_dp, ctypes.c_size_t, ctypes.c_uint64, _ip, ctypes.c_int,
+                                             ctypes.c_int, _ip]
         lib.ref_adapt_interferometer.restype = ctypes.c_int
         lib.ref_adapt_interferometer.argtypes = [_dp, ctypes.c_size_t, _ip, _ip, _dp,
                                                  ctypes.POINTER(ctypes.c_size_t),
@@ -131,4 +140,34 @@ def simulate_B(u, seed, input_state, shots):
     i, pi = _s(input_state)
     out = np.zeros((shots, u.shape[0]), dtype=np.int64)
     _check(load().ref_simulate_B(pu, u.shape[0], seed, pi, shots, out.ctypes.data_as(_ip)))
+    return out
+
+
+def simulate_B_two_calls(u, seed, input_state, shots1, shots2):
+    """One strategy object, seed(seed), then simulate(input, shots1) and simulate(input, shots2):
+    the global generator keeps running between the calls."""
+    u, pu = _m(u)
+    i, pi = _s(input_state)
+    out = np.zeros((shots1 + shots2, u.shape[0]), dtype=np.int64)
+    _check(load().ref_simulate_B_two_calls(pu, u.shape[0], seed, pi, shots1, shots2, out.ctypes.data_as(_ip)))
+    return out
+
+
+def simulate_B_uniform_losses(u, seed, input_state, shots, transmittance):
+    """CGeneralizedCliffordsBUniformLossesSimulationStrategy(U, transmittance, 0); seed; simulate."""
+    u, pu = _m(u)
+    i, pi = _s(input_state)
+    out = np.zeros((shots, u.shape[0]), dtype=np.int64)
+    _check(load().ref_simulate_B_uniform_losses(pu, u.shape[0], seed, pi, shots, transmittance,
+                                                out.ctypes.data_as(_ip)))
+    return out
+
+
+def simulate_B_lossy(u, seed, input_state, shots, approximated_modes):
+    """CGeneralizedCliffordsBLossySimulationStrategy(U, approximated_modes, 0); seed; simulate."""
+    u, pu = _m(u)
+    i, pi = _s(input_state)
+    out = np.zeros((shots, u.shape[0]), dtype=np.int64)
+    _check(load().ref_simulate_B_lossy(pu, u.shape[0], seed, pi, shots, approximated_modes,
+                                       out.ctypes.data_as(_ip)))
     return out

@@ -8,8 +8,12 @@ from . import _lib
 from ._lib import Pqb200Error, last_stats, load
 from .Boson_Sampling_Utilities import *  # noqa: F401,F403
 from .simulation_strategies import (  # noqa: F401
+    GeneralizedCliffordsBLossySimulationStrategy,
+    GeneralizedCliffordsBLossySimulationStrategy_wrapper,
     GeneralizedCliffordsBSimulationStrategy,
     GeneralizedCliffordsBSimulationStrategy_wrapper,
+    GeneralizedCliffordsBUniformLossesSimulationStrategy,
+    GeneralizedCliffordsBUniformLossesSimulationStrategy_wrapper,
     compute_pmf,
 )
 

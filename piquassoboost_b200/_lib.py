@@ -74,6 +74,33 @@ _SIGNATURES = {
         [c_double_p, ctypes.c_size_t, ctypes.c_size_t, c_int64_p, ctypes.c_size_t, ctypes.c_uint64,
          ctypes.c_int, c_int64_p],
     ),
+    "pqb200_pmf_layer_batched": (
+        ctypes.c_int,
+        [c_double_p, ctypes.c_size_t, ctypes.c_size_t, c_int64_p, c_int64_p, ctypes.c_size_t,
+         ctypes.c_int, c_double_p],
+    ),
+    "pqb200_seed": (ctypes.c_int, [ctypes.c_uint64]),
+    "pqb200_fill_r_samples": (
+        ctypes.c_int,
+        [c_double_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t,
+         ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint8), c_double_p, ctypes.c_int,
+         c_int64_p],
+    ),
+    "pqb200_simulate_B_next": (
+        ctypes.c_int,
+        [c_double_p, ctypes.c_size_t, ctypes.c_size_t, c_int64_p, ctypes.c_size_t, ctypes.c_int,
+         c_int64_p],
+    ),
+    "pqb200_simulate_B_uniform_losses": (
+        ctypes.c_int,
+        [c_double_p, ctypes.c_size_t, ctypes.c_size_t, c_int64_p, ctypes.c_size_t, ctypes.c_double,
+         ctypes.c_int, c_int64_p],
+    ),
+    "pqb200_simulate_B_lossy": (
+        ctypes.c_int,
+        [c_double_p, ctypes.c_size_t, ctypes.c_size_t, c_int64_p, ctypes.c_size_t, ctypes.c_int,
+         ctypes.c_int, c_double_p, c_int64_p],
+    ),
     "pqb200_last_stats": (ctypes.c_int, [ctypes.POINTER(Pqb200Stats)]),
     "pqb200_fp64_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_double, c_double_p]),
 }

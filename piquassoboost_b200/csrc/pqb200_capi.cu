@@ -21,6 +21,8 @@
 #include "dd.cuh"
 #include "launch.h"
 #include "batch_host.h"
+#include "laplace_host.h"
+#include "svd_host.h"
 #include "repeated_host.h"
 
 using namespace pqb200;
@@ -329,6 +331,8 @@ void combine_partials(const double* parts, size_t count, size_t rows, double out
 
 extern "C" {
 
+static void lap_release_all();
+
 const char* pqb200_last_error(void) { return g_err.c_str(); }
 const char* pqb200_version(void) { return "pqb200 0.1 (sm_100a)"; }
 
@@ -360,6 +364,7 @@ void pqb200_shutdown(void) {
         cudaEventDestroy(c.e1);
         cudaStreamDestroy(c.stream);
     }
+    lap_release_all();
     g_devs.clear();
     g_visible = -1;
     g_default_ndev = 0;
@@ -557,6 +562,8 @@ static int grow(void** p, size_t* cap, size_t need) {
     *cap = want;
     return PQB200_OK;
 }
+
+#include "sampler_capi.inc"
 
 struct BatchItem {
     BatchJobHost job;
@@ -916,69 +923,27 @@ int pqb200_pmf_layer(const double* u, size_t m, size_t stride, const int64_t* sa
     int rc = ensure_devices(ndev, &used);
     if (rc) return rc;
     g_stats = {0.0, 0.0, 0, used};
+    // all sub-permanents of a shot in one Gray sweep (laplace_sampler.cuh); shots beyond that
+    // kernel's photon limit fall through to one batched job per sub-permanent
+    rc = pmf_layer_laplace_locked(u, m, stride, samples, inputs, S, used, pmf);
+    if (rc != -1) return rc;
     return pmf_layer_locked(u, m, stride, samples, inputs, S, used, pmf);
 }
 
-int pqb200_simulate_B(const double* u, size_t m, size_t stride, const int64_t* input_state,
-                      size_t shots, uint64_t seed, int ndev, int64_t* samples_out) {
-    if (!u || !input_state || (shots && !samples_out)) return fail(PQB200_ERR_ARG, "null pointer");
+// The same layer with one batched kernel job per sub-permanent (k repeated permanents per shot, as
+// compute_pmf itself does): kept as the cross-check of the single-sweep kernel and for > 40 photons.
+int pqb200_pmf_layer_batched(const double* u, size_t m, size_t stride, const int64_t* samples,
+                             const int64_t* inputs, size_t S, int ndev, double* pmf) {
+    if (!u || !samples || !inputs || !pmf) return fail(PQB200_ERR_ARG, "null pointer");
     if (m == 0 || m > 255) return fail(PQB200_ERR_ARG, "number of modes must be in 1..255");
     if (stride < m) return fail(PQB200_ERR_ARG, "stride is smaller than the number of modes");
-    int64_t nphot = 0;
-    for (size_t i = 0; i < m; i++) {
-        if (input_state[i] < 0) return fail(PQB200_ERR_ARG, "negative occupation number");
-        nphot += input_state[i];
-    }
-    if (shots == 0) return PQB200_OK;
+    if (S == 0) return PQB200_OK;
     std::lock_guard<std::mutex> lk(g_mu);
     int used = 0;
     int rc = ensure_devices(ndev, &used);
     if (rc) return rc;
     g_stats = {0.0, 0.0, 0, used};
-    // The reference draws exactly two numbers per photon step per shot from ONE std::mt19937, shot
-    // after shot (samplingHelperFunctions.cpp:58-74,355,389): pre-generate them in that order so
-    // that all shots can advance through photon step k together.
-    std::mt19937 rng(static_cast<std::mt19937::result_type>(seed));
-    std::vector<uint32_t> draws(shots * 2 * (size_t)nphot);
-    for (auto& d : draws) d = (uint32_t)rng();
-    std::vector<int64_t> cur(shots * m, 0), work(shots * m);
-    for (size_t s = 0; s < shots; s++) memcpy(&work[s * m], input_state, m * sizeof(int64_t));
-    memset(samples_out, 0, shots * m * sizeof(int64_t));
-    std::vector<double> pmf(shots * m);
-    for (int64_t k = 0; k < nphot; k++) {
-        const uint32_t left = (uint32_t)(nphot - k);
-        for (size_t s = 0; s < shots; s++) {
-            // update_input_by_single_photon (samplingHelperFunctions.cpp:377-406): the
-            // (rng() % left)-th not-yet-inserted photon, photons listed in mode order
-            uint32_t pick = draws[(s * (size_t)nphot + (size_t)k) * 2] % left;
-            int64_t* w = &work[s * m];
-            for (size_t i = 0; i < m; i++) {
-                if ((int64_t)pick < w[i]) {
-                    w[i]--;
-                    cur[s * m + i]++;
-                    break;
-                }
-                pick -= (uint32_t)w[i];
-            }
-        }
-        rc = pmf_layer_locked(u, m, stride, samples_out, cur.data(), shots, used, pmf.data());
-        if (rc) return rc;
-        for (size_t s = 0; s < shots; s++) {
-            // sample_from_pmf (samplingHelperFunctions.cpp:350-374)
-            const double r = (double)draws[(s * (size_t)nphot + (size_t)k) * 2 + 1] / 4294967295.0;
-            size_t chosen = 0;
-            double acc = 0.0;
-            for (size_t i = 0; i < m; i++) {
-                acc += pmf[s * m + i];
-                if (acc >= r) {
-                    chosen = i;
-                    break;
-                }
-            }
-            samples_out[s * m + chosen]++;
-        }
-    }
-    return PQB200_OK;
+    return pmf_layer_locked(u, m, stride, samples, inputs, S, used, pmf);
 }
 
 }  // extern "C"

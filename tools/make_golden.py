@@ -91,6 +91,36 @@ def kats_from_reference_tests():
         sys.modules.pop("numpy_proxy", None)
 
 
+def lossy_expected_from_reference_tests():
+    """expected_samples of the two LossyInterferometer tests of unittests/test_seeding.py."""
+    import ast
+    tree = ast.parse(open(os.path.join(REF, "unittests", "test_seeding.py")).read())
+    out = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in (
+                "test_LossyInterferometer_boson_sampling_seeded",
+                "test_LossyInterferometer_boson_sampling_uniform_losses"):
+            for sub in ast.walk(node):
+                if isinstance(sub, ast.Assign) and getattr(sub.targets[0], "id", None) == "expected_samples":
+                    out[node.name] = [list(t) for t in ast.literal_eval(sub.value)]
+    assert len(out) == 2
+    return out
+
+
+def expanded_space(interferometer_svd):
+    """piquasso-module/piquasso/_simulators/sampling/utils.py:443-474 (the 2m x 2m unitary dilation
+    piquassoboost/sampling/calculations.py:125-135 feeds to the lossless B strategy), executed from
+    the reference source itself."""
+    import ast
+    src = open(os.path.join(REF, "piquasso-module", "piquasso", "_simulators", "sampling", "utils.py")).read()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in (
+        "_prepare_interferometer_matrix_in_expanded_space", "_calculate_singular_values_matrix_expansion")]
+    g = {"np": np}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "utils.py", "exec"), g)
+    return g["_prepare_interferometer_matrix_in_expanded_space"](interferometer_svd)
+
+
 def seeding_from_reference_tests():
     """_U and the expected lossless shots of unittests/test_seeding.py (seed 123)."""
     src = open(os.path.join(REF, "unittests", "test_seeding.py")).read()
@@ -197,6 +227,50 @@ def main():
                "pmf_rows": pmfs, "source": "unittests/test_seeding.py:51-83"},
               open(os.path.join(OUT, "sampling_seed123.json"), "w"), indent=1)
     print("sampler golden ok; first shots", cpp[:3].tolist())
+
+    # ---- 5. lossy strategies.  (a) the reference's own two LossyInterferometer KATs
+    # (unittests/test_seeding.py:88-165) replayed through the call chain of
+    # piquassoboost/sampling/calculations.py:105-152; (b) direct runs of the three strategies.
+    exp = lossy_expected_from_reference_tests()
+    inp = [2, 1, 1, 0, 1]
+    lossy = {"input": inp, "seed": 123, "shots": 20, "source": "unittests/test_seeding.py:88-165"}
+    # uniform: interferometer / s0 with transmissivity s0
+    M = U @ np.diag([0.9] * 5) @ U @ U.T
+    sv = np.linalg.svd(M)
+    got = refbind.simulate_B_uniform_losses(np.ascontiguousarray(M / sv[1][0]), 123, inp, 20, float(sv[1][0]))
+    want = exp["test_LossyInterferometer_boson_sampling_uniform_losses"]
+    assert sorted(map(tuple, got.tolist())) == sorted(map(tuple, want)), "uniform-loss KAT mismatch"
+    lossy["uniform"] = {"matrix": c2l(M / sv[1][0]), "transmissivity": float(sv[1][0]),
+                        "cpp_generation_order": got.tolist(), "expected_python_order": want}
+    # non-uniform: lossless B strategy on the 2m x 2m dilation, samples trimmed to m modes
+    M = U @ np.diag([0.9, 0.8, 0.7, 0.6, 0.5]) @ U @ U.T
+    E = np.ascontiguousarray(expanded_space(np.linalg.svd(M)))
+    got = refbind.simulate_B(E, 123, inp + [0] * 5, 20)
+    want = exp["test_LossyInterferometer_boson_sampling_seeded"]
+    assert sorted(map(tuple, got[:, :5].tolist())) == sorted(map(tuple, want)), "lossy KAT mismatch"
+    lossy["dilation"] = {"matrix": c2l(E), "input": inp + [0] * 5, "cpp_generation_order": got.tolist(),
+                         "expected_python_order_trimmed": want}
+    # direct strategy runs on seeded inputs
+    runs = []
+    for idx, (m, n_in, shots) in enumerate([(6, 5, 30), (8, 6, 30), (10, 8, 20)]):
+        V = unitary_group.rvs(m, random_state=300 + idx)
+        rng = np.random.default_rng(300 + idx)
+        state = rng.multinomial(n_in - 1, [1 / m] * m)
+        state[idx % 2] += 1  # the reference dereferences an empty table when the approximated modes hold no photon
+        state = state.tolist()
+        loss = V * rng.uniform(0.6, 0.95, size=m)[:, None]
+        seed = 1000 + idx
+        runs.append({
+            "m": m, "input": state, "seed": seed, "shots": shots, "unitary": c2l(V), "lossy_matrix": c2l(loss),
+            "uniform_losses": {"transmissivity": 0.8,
+                               "samples": refbind.simulate_B_uniform_losses(V, seed, state, shots, 0.8).tolist()},
+            "lossy_0": refbind.simulate_B_lossy(loss, seed, state, shots, 0).tolist(),
+            "lossy_2": refbind.simulate_B_lossy(loss, seed, state, shots, 2).tolist(),
+            "two_calls": refbind.simulate_B_two_calls(V, seed, state, 7, shots - 7).tolist(),
+        })
+    lossy["runs"] = runs
+    json.dump(lossy, open(os.path.join(OUT, "sampling_lossy.json"), "w"))
+    print("lossy golden ok")
 
 
 if __name__ == "__main__":
