@@ -66,6 +66,15 @@ int pqb200_permanent_shard(const double* a, size_t rows, size_t cols, size_t str
  * exact 2^-(rows-1) scaling (reference: BBFGPermanentCalculator.hpp:227-232). */
 int pqb200_permanent_combine(const double* partials_dd, size_t count, size_t rows, double out[2]);
 
+/* perm(A) of a square matrix (2 <= n <= 45) with EVERY operation in double-double arithmetic
+ * (~106 mantissa bits): the engine's counterpart of the reference's extended-precision request
+ *   BBFGPermanentCalculator::calculate(mtx, use_extended=true)  sampling/source/BBFGPermanentCalculator.cpp:109-116
+ * (x87 long double there).  About 25x slower than pqb200_permanent; it exists to give ground truth at
+ * sizes the CPU reference cannot reach (n=40) and is sharded over `ndev` devices the same way.
+ * out_dd = re.hi re.lo im.hi im.lo of the scaled permanent. */
+int pqb200_permanent_dd(const double* a, size_t rows, size_t cols, size_t stride, int ndev,
+                        double out_dd[4]);
+
 /* Many plain permanents in one call: count matrices, matrix k is rows[k] x cols[k] with stride
  * strides[k].  Replaces the list-of-matrices branch of the Python wrapper
  * (sampling/GlynnPermanentCalculator_Wrapper.hpp:204-293). */

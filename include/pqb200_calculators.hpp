@@ -13,6 +13,7 @@
 //   GlynnPermanentCalculatorSimple<M,P>::calculate(mtx)            sampling/source/GlynnPermanentCalculatorSimple.hpp:47-53
 //   BBFGPermanentCalculatorRepeated::calculate(mtx, col, row, ..)  sampling/source/BBFGPermanentCalculatorRepeated.cpp:74-141
 //   GlynnPermanentCalculatorRepeated<M,P>::calculate(mtx, in, out) sampling/source/GlynnPermanentCalculatorRepeated.hpp:49-74
+//   BatchednPermanentCalculator::{add,calculate,reserve_space,clear} sampling/source/BatchedPermanentCalculator.cpp:81-100,109-296,304-325
 //   compute_pmf(U, sample, current_input)                          sampling/simulation_strategies/source/samplingHelperFunctions.cpp:78-342
 #pragma once
 #include <complex>
@@ -94,6 +95,67 @@ public:
 };
 using GlynnPermanentCalculatorRepeatedDouble = GlynnPermanentCalculatorRepeated;
 using GlynnPermanentCalculatorRepeatedLongDouble = GlynnPermanentCalculatorRepeated;
+
+/// Accumulates (input_state, output_state) pairs against one interferometer and evaluates them in ONE
+/// batched call (BatchedPermanentCalculator.cpp:81-100,109-296; there: a CPU loop or DFE batches).
+/// As in the reference the states are borrowed pointers that must outlive calculate(), the container
+/// must be sized with reserve_space() before add(), and calculate() clears the list.
+template <class Matrix, class State>
+class BatchednPermanentCalculator {
+public:
+    BatchednPermanentCalculator() : mtx_(nullptr) {}
+    explicit BatchednPermanentCalculator(Matrix& interferometer_matrix_in) : mtx_(&interferometer_matrix_in) {}
+
+    void reserve_space(size_t num_of_permanents) {
+        input_states_.resize(num_of_permanents, nullptr);
+        output_states_.resize(num_of_permanents, nullptr);
+    }
+
+    void add(State* input_state, State* output_state, size_t index) {
+        int64_t si = 0, so = 0;
+        for (size_t i = 0; i < input_state->size(); i++) si += (int64_t)(*input_state)[i];
+        for (size_t i = 0; i < output_state->size(); i++) so += (int64_t)(*output_state)[i];
+        if (si != so)
+            throw std::string("BatchednPermanentCalculator::add:  Number of input and output states should be equal");
+        if (index >= input_states_.size() || index >= output_states_.size())
+            throw std::string("BatchednPermanentCalculator::add:  Containers must be resized");
+        input_states_[index] = input_state;
+        output_states_[index] = output_state;
+    }
+
+    /// every supported `lib` id runs the CUDA engine; returns the permanents in insertion order
+    std::vector<Complex16> calculate(int lib = 0) {
+        (void)lib;
+        if (!mtx_ || mtx_->rows == 0 || mtx_->cols == 0)
+            throw std::string("BatchednPermanentCalculator::calculate:  interferometer matrix is zero");
+        const size_t count = input_states_.size(), R = mtx_->rows, C = mtx_->cols;
+        std::vector<int64_t> rm(count * R), cm(count * C);
+        for (size_t k = 0; k < count; k++) {
+            if (!input_states_[k] || !output_states_[k])
+                throw std::string("BatchednPermanentCalculator::calculate:  unset state pair");
+            for (size_t i = 0; i < R; i++) rm[k * R + i] = (int64_t)(*output_states_[k])[i];
+            for (size_t j = 0; j < C; j++) cm[k * C + j] = (int64_t)(*input_states_[k])[j];
+        }
+        std::vector<double> out(2 * count);
+        if (count)
+            check(pqb200_permanent_repeated_batch(reinterpret_cast<const double*>(mtx_->get_data()), R, C,
+                                                  mtx_->stride, rm.data(), cm.data(), count,
+                                                  default_ndev(), out.data()));
+        std::vector<Complex16> ret(count);
+        for (size_t k = 0; k < count; k++) ret[k] = Complex16(out[2 * k], out[2 * k + 1]);
+        clear();
+        return ret;
+    }
+
+    void clear() {
+        input_states_.clear();
+        output_states_.clear();
+    }
+
+private:
+    Matrix* mtx_;
+    std::vector<State*> input_states_, output_states_;
+};
 
 /// compute_pmf for one shot; returns m probabilities
 template <class Matrix, class State>

@@ -245,3 +245,16 @@ def permanent_CPU_repeated_double(matrix, input_state, output_state):
 def permanent_CPU_repeated_long_double(matrix, input_state, output_state):
     """sampling/permanent_calculators_wrapper.cpp:157-160."""
     return _repeated_permanent(matrix, input_state, output_state, DEFAULT_NDEV)
+
+
+def permanent_double_double(matrix, ndev=None):
+    """perm(matrix) with every operation in double-double arithmetic (`pqb200_permanent_dd`): the
+    engine's extended-precision evaluation (cf. BBFGPermanentCalculator.cpp:109-116, long double in
+    the reference).  Returns `(value, parts)`: the value rounded to complex128 and the four doubles
+    re.hi, re.lo, im.hi, im.lo."""
+    m = _lib.as_matrix(matrix)
+    parts = np.zeros(4, dtype=np.float64)
+    _lib.check(_lib.load().pqb200_permanent_dd(
+        _lib.dptr(m), m.shape[0], m.shape[1], m.strides[0] // 16 if m.shape[1] else 0,
+        DEFAULT_NDEV if ndev is None else int(ndev), _lib.dptr(parts)))
+    return complex(parts[0] + parts[1], parts[2] + parts[3]), parts

@@ -42,6 +42,10 @@ _SIGNATURES = {
         ctypes.c_int,
         [c_double_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, c_double_p],
     ),
+    "pqb200_permanent_dd": (
+        ctypes.c_int,
+        [c_double_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, c_double_p],
+    ),
     "pqb200_permanent_shard": (
         ctypes.c_int,
         [c_double_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,

@@ -60,6 +60,18 @@ __host__ __device__ __forceinline__ dd dd_mul_d(const dd& x, double f) {
     return r;
 }
 
+// x * y, both double-double (relative error ~ 2^-104)
+__host__ __device__ __forceinline__ dd dd_mul_dd(const dd& x, const dd& y) {
+    const double p = x.hi * y.hi;
+    double e = fma(x.hi, y.hi, -p);
+    e = fma(x.hi, y.lo, e);
+    e = fma(x.lo, y.hi, e);
+    dd r;
+    r.hi = p + e;
+    r.lo = e - (r.hi - p);
+    return r;
+}
+
 __host__ __device__ __forceinline__ dd dd_neg(const dd& x) {
     dd r;
     r.hi = -x.hi;
@@ -70,6 +82,16 @@ __host__ __device__ __forceinline__ dd dd_neg(const dd& x) {
 __host__ __device__ __forceinline__ void cdd_add(cdd& acc, const cdd& x) {
     dd_add_dd(acc.re, x.re);
     dd_add_dd(acc.im, x.im);
+}
+
+// complex dd product
+__host__ __device__ __forceinline__ cdd cdd_mul(const cdd& x, const cdd& y) {
+    cdd r;
+    r.re = dd_mul_dd(x.re, y.re);
+    dd_add_dd(r.re, dd_neg(dd_mul_dd(x.im, y.im)));
+    r.im = dd_mul_dd(x.re, y.im);
+    dd_add_dd(r.im, dd_mul_dd(x.im, y.re));
+    return r;
 }
 
 __host__ __device__ __forceinline__ cdd cdd_zero() {

@@ -16,9 +16,14 @@
 //     registers spent on row data.  All loops have warp-uniform trip counts so that the compiler
 //     can keep the row index in the uniform datapath; threads past the end of the chunk range run
 //     a dummy chunk whose sum is discarded;
-//   * per step: 2N DADD/DFMA (column update) + 4(N-1) DMUL/DFMA (complex product chains; the last
-//     complex multiply is fused into the accumulator) = 6N-4 FP64 instructions for 8N algorithmic
-//     flops;
+//   * the host normalises the matrix with unit-modulus row/column factors (plain_host.h) so that the
+//     LAST ROW (the row the Gray code toggles at every second step) and the LAST COLUMN are real:
+//     the fast toggle then updates real parts only (N DADD instead of 2N) and the last factor of the
+//     product is a real number fused into the accumulate (2 DFMA).  The unit-modulus correction
+//     factor is applied once, in double-double, by the CTA that finishes the grid reduction;
+//   * per step: (N + 2N-1)/2 DFMA (column update, averaged over fast/general toggles) + 4(N-2) + 2
+//     DMUL/DFMA (complex product chains) = 5.5N-6.5 FP64 instructions for 8N algorithmic flops
+//     (a straight complex evaluation needs 6N-4);
 //   * every DDP (default 8) terms the partial sum is folded into a double-double accumulator (TwoSum), chunk sums
 //     are combined per thread in dd, then warp shuffle -> shared -> one partial per CTA -> the last
 //     CTA reduces all partials in a fixed order (deterministic) into 4 doubles (re.hi re.lo im.hi
@@ -45,6 +50,9 @@ struct PlainParams {
     double* partials;                           // [gridDim.x][4]
     unsigned int* counter;                      // zero on entry, reset to zero on exit
     double* out;  // 4 doubles: re.hi re.lo im.hi im.lo  (unscaled sum over the chunk range)
+    double phase[4];  // unit-modulus correction factor (re.hi re.lo im.hi im.lo) applied to the sum
+    int fast_row;     // == 0 (index of the real row); a run-time value for the rolled kernel, whose
+                      // schedule is better when ptxas cannot turn the row loads into immediates
 };
 
 __device__ __forceinline__ double shfl_down_d(double v, int off) {
@@ -68,7 +76,7 @@ __device__ __forceinline__ cdd warp_reduce_cdd(cdd v) {
 // Deterministic: every level sums in a fixed order.
 template <int THREADS>
 __device__ __noinline__ void grid_reduce_cdd(cdd tot, double* partials, unsigned int* counter,
-                                             double* out) {
+                                             double* out, const double* phase = nullptr) {
     __shared__ double s_red[THREADS / 32][4];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -114,6 +122,14 @@ __device__ __noinline__ void grid_reduce_cdd(cdd tot, double* partials, unsigned
         }
         b = warp_reduce_cdd(b);
         if (lane == 0) {
+            if (phase) {
+                cdd f;
+                f.re.hi = phase[0];
+                f.re.lo = phase[1];
+                f.im.hi = phase[2];
+                f.im.lo = phase[3];
+                b = cdd_mul(b, f);
+            }
             out[0] = b.re.hi;
             out[1] = b.re.lo;
             out[2] = b.im.hi;
@@ -149,55 +165,248 @@ __device__ __forceinline__ void cmul(double& xr, double& xi, double yr, double y
     xi = i;
 }
 
-// One Gray term: acc += (NEG ? -1 : +1) * prod_j c[j], with CH independent multiply chains for ILP.
-// multiply chains per term, tuned on B200 (tools/microbench/mb2.cu, profiles/mb2_r1.log): long products
-// want few chains (register pressure at N >= 36), short ones want many (latency)
+// Loop form and multiply-chain count per N: the argmin of the measured sweep
+// tools/microbench/tune_plain.cu on B200 (profiles/tune_plain_r1.log).  The FP64 pipe only stays fed
+// if ptxas interleaves the dependent multiply chains with the independent column updates, and how
+// well it does that depends on N (register pressure) -- so the choice is tabulated, not modelled.
+//   unroll 2   : rolled kernel (glynn_plain_rolled_kernel), best when the column sums alone take
+//                >= 136 registers;   unroll 4 / 8 : terms per iteration of glynn_plain_kernel.
+__host__ __device__ constexpr int default_unroll(int n) {
+    return n >= 34 ? 2 : (n >= 17 && n <= 22) ? 4 : 8;
+}
 __host__ __device__ constexpr int default_chains(int n) {
-    return n >= 36 ? 2 : n >= 26 ? 4 : n >= 18 ? 8 : n >= 8 ? 4 : n >= 4 ? 2 : 1;
+    return n >= 45 ? 2 : n == 44 ? 4 : n == 43 ? 6 : n == 42 ? 3 : n == 41 ? 8 : n == 40 ? 4 : n == 39 ? 3
+         : n == 38 ? 4 : n == 37 ? 8 : n == 36 ? 6 : n == 35 ? 2 : n == 34 ? 8 : n == 33 ? 4 : n == 32 ? 8
+         : n == 31 ? 4 : n == 30 ? 2 : n == 29 ? 8 : n >= 23 ? 4 : n >= 17 ? 2 : n >= 8 ? 4 : n >= 4 ? 2 : 1;
 }
 
-template <int N, bool NEG, int CH = default_chains(N)>
-__device__ __forceinline__ void term_acc(const double (&cr)[N], const double (&ci)[N],
-                                         double& acc_re, double& acc_im) {
-    if (N == 1) {
-        acc_re += NEG ? -cr[0] : cr[0];
-        acc_im += NEG ? -ci[0] : ci[0];
-        return;
-    }
-    double qr[CH], qi[CH];
+// column update  x <- x + sign * a   with  SIGNMODE 0: sign = +1 and 1: sign = -1 at compile time (DADD
+// with the matrix element as an immediate constant-bank operand), 2: sign = sg at run time (DFMA)
+template <int SIGNMODE>
+__device__ __forceinline__ double upd(double x, double a, double sg) {
+    return SIGNMODE == 0 ? x + a : SIGNMODE == 1 ? x - a : fma(sg, a, x);
+}
+
+// One Gray term, acc += (NEG ? -1 : +1) * prod_j c[j], fused with the toggle of row `row` into the
+// next term: column j is updated right after its last use in the product, so that the independent
+// update instructions sit between the dependent multiplies of the CH chains (they hide the FP64
+// latency; 8 warps per SM cannot).  Columns 0..N-2 are complex, column N-1 is real (ci[N-1] is never
+// touched) and is fused into the accumulate.  REALROW: the toggled row is real (Gray bit 0).
+template <int N, bool NEG, int CH, bool REALROW, int SIGNMODE>
+__device__ __forceinline__ void term_toggle(const PlainParams<N>& p, int row, double sg,
+                                            double (&cr)[N], double (&ci)[N], double& acc_re,
+                                            double& acc_im) {
+    constexpr int M = N - 1;  // complex factors
+    constexpr int C = CH < M ? CH : M;
+    double qr[C], qi[C];
 #pragma unroll
-    for (int k = 0; k < CH; k++) {
+    for (int k = 0; k < C; k++) {
         qr[k] = cr[k];
         qi[k] = ci[k];
+        cr[k] = upd<SIGNMODE>(cr[k], p.A2[row][k].x, sg);
+        if (!REALROW) ci[k] = upd<SIGNMODE>(ci[k], p.A2[row][k].y, sg);
     }
-    // one factor is left out of the chains so that the last multiply can be fused into the accumulate
 #pragma unroll
-    for (int j = CH; j < N - 1; j++) cmul(qr[j % CH], qi[j % CH], cr[j], ci[j]);
-    // combine the chains pairwise
-#pragma unroll
-    for (int w = 1; w < CH; w *= 2) {
-#pragma unroll
-        for (int k = 0; k + w < CH; k += 2 * w) cmul(qr[k], qi[k], qr[k + w], qi[k + w]);
+    for (int j = C; j < M; j++) {
+        cmul(qr[j % C], qi[j % C], cr[j], ci[j]);
+        cr[j] = upd<SIGNMODE>(cr[j], p.A2[row][j].x, sg);
+        if (!REALROW) ci[j] = upd<SIGNMODE>(ci[j], p.A2[row][j].y, sg);
     }
-    cmul_acc<NEG>(acc_re, acc_im, qr[0], qi[0], cr[N - 1], ci[N - 1]);
+#pragma unroll
+    for (int w = 1; w < C; w *= 2) {
+#pragma unroll
+        for (int k = 0; k + w < C; k += 2 * w) cmul(qr[k], qi[k], qr[k + w], qi[k + w]);
+    }
+    const double f = NEG ? -cr[N - 1] : cr[N - 1];
+    cr[N - 1] = upd<SIGNMODE>(cr[N - 1], p.A2[row][N - 1].x, sg);
+    acc_re = fma(qr[0], f, acc_re);
+    acc_im = fma(qi[0], f, acc_im);
 }
 
-// c += sg * row   (sg = +-1 (or +-0.5 when seeding) in a register; row in uniform registers)
+// c += sg * row (seeding and the rare mid-chunk correction)
 template <int N>
 __device__ __forceinline__ void toggle_row(const PlainParams<N>& p, int row, double sg,
                                            double (&cr)[N], double (&ci)[N]) {
 #pragma unroll
     for (int j = 0; j < N; j++) {
         cr[j] = fma(sg, p.A2[row][j].x, cr[j]);
-        ci[j] = fma(sg, p.A2[row][j].y, ci[j]);
+        if (j < N - 1) ci[j] = fma(sg, p.A2[row][j].y, ci[j]);
     }
 }
 
-// DDP: the partial sum is folded into the double-double accumulator every DDP terms (a power of two
-// >= 2); CH: independent multiply chains per term.
-template <int N, int DDP = 8, int CH = default_chains(N)>
+// chunk accumulator (re.hi re.lo im.hi im.lo at stride kPlainThreads in shared memory) += (re, im)
+__device__ __forceinline__ void fold_chunk_acc(double* acc, double re, double im) {
+    dd a;
+    a.hi = acc[0 * kPlainThreads];
+    a.lo = acc[1 * kPlainThreads];
+    dd_add_d(a, re);
+    acc[0 * kPlainThreads] = a.hi;
+    acc[1 * kPlainThreads] = a.lo;
+    a.hi = acc[2 * kPlainThreads];
+    a.lo = acc[3 * kPlainThreads];
+    dd_add_d(a, im);
+    acc[2 * kPlainThreads] = a.hi;
+    acc[3 * kPlainThreads] = a.lo;
+}
+
+__host__ __device__ constexpr int ctz_c(int x) { return (x & 1) ? 0 : 1 + ctz_c(x >> 1); }
+
+// +-1.0 assembled from integer bits: -1.0 with the sign flipped when `bit` is set.  `vzero` is always
+// zero but thread-dependent as far as the compiler can tell: it keeps the factor in a VECTOR register
+// while the step counter that `bit` comes from never leaves the uniform datapath.
+__device__ __forceinline__ double pm_one(unsigned int bit, unsigned int vzero) {
+    return __hiloint2double((int)((0xbff00000u ^ (bit << 31)) ^ vzero), 0);
+}
+
+// Terms T..U-1 of one unrolled group of U = 2^LOGU consecutive Gray terms starting at local step s
+// (s is a multiple of U).  Which row a term toggles, and for most of them the direction, depend on
+// T alone: those rows are read as immediate constant-bank operands with the sign folded into the
+// instruction.  Only the last toggle of the group (Gray bit >= LOGU) has a run-time row.
+template <int N, int CH, int U, int T>
+struct UnrolledTerms {
+    static __device__ __forceinline__ void run(const PlainParams<N>& p, unsigned int s,
+                                               unsigned int vzero, double (&cr)[N], double (&ci)[N],
+                                               double& acc_re, double& acc_im) {
+        constexpr bool NEG = (T & 1) != 0;
+        if constexpr ((T & 1) == 0) {
+            // into an odd term: Gray bit 0 (real row 0) is set iff bit 1 of the even index is clear
+            term_toggle<N, NEG, CH, true, ((T >> 1) & 1) ? 0 : 1>(p, 0, 0.0, cr, ci, acc_re, acc_im);
+        } else if constexpr (T + 1 < U) {
+            // into the even term s+T+1: Gray bit b = ctz(T+1) changes, set iff bit b+1 of it is clear
+            constexpr int b = ctz_c(T + 1);
+            if constexpr ((2 << b) < U) {
+                term_toggle<N, NEG, CH, false, (((T + 1) >> (b + 1)) & 1) ? 0 : 1>(p, b, 0.0, cr, ci, acc_re, acc_im);
+            } else {  // bit b+1 == LOGU of s+T+1 is bit LOGU of s
+                const double sg = pm_one((s / U) & 1u, vzero);
+                term_toggle<N, NEG, CH, false, 2>(p, b, sg, cr, ci, acc_re, acc_im);
+            }
+        } else {
+            const unsigned int s2 = s + U;
+            const int b = __ffs(s2) - 1;
+            const double sg = pm_one((s2 >> (b + 1)) & 1u, vzero);
+            term_toggle<N, NEG, CH, false, 2>(p, b, sg, cr, ci, acc_re, acc_im);
+        }
+        if constexpr (T + 1 < U) UnrolledTerms<N, CH, U, T + 1>::run(p, s, vzero, cr, ci, acc_re, acc_im);
+    }
+};
+
+// CH: independent multiply chains per term; U: terms per iteration of the unrolled chunk loop (the
+// partial sum is folded into the double-double accumulator once per iteration).
+template <int N, int CH = default_chains(N), int U = default_unroll(N)>
 __global__ void __launch_bounds__(kPlainThreads, 1)
 glynn_plain_kernel(const __grid_constant__ PlainParams<N> p) {
+    const int rows = p.rows;
+    const int L = p.L;
+    const unsigned int nsteps = 1u << L;
+    const unsigned long long nthreads = (unsigned long long)gridDim.x * kPlainThreads;
+    // The double-double accumulators are touched once per U terms (chunk sum) / once per chunk
+    // (thread total): they live in shared memory, not in the register file the column sums need.
+    __shared__ double s_acc[8][kPlainThreads];
+    double* const acc = &s_acc[0][threadIdx.x];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k * kPlainThreads] = 0.0;
+    unsigned long long c =
+        p.chunk_begin + (unsigned long long)blockIdx.x * kPlainThreads + threadIdx.x;
+    for (unsigned int it = 0; it < p.iters; it++, c += nthreads) {
+        const bool live = c < p.chunk_end;
+        const unsigned long long cc = live ? c : p.chunk_begin;
+        const unsigned long long g0 = cc << L;
+        const unsigned long long gray0 = g0 ^ (g0 >> 1);
+        // ---- seed the column sums from the chunk's start code (reference: BBFG...hpp:136-176).
+        // Row order in A2: index k < rows-1 is the row of Gray bit k, index rows-1 the delta=+1 row.
+        double cr[N], ci[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            cr[j] = 0.5 * p.A2[rows - 1][j].x;
+            if (j < N - 1) ci[j] = 0.5 * p.A2[rows - 1][j].y;
+        }
+#pragma unroll 1
+        for (int k = 0; k < rows - 1; k++) {
+            const double d = ((gray0 >> k) & 1ull) ? -0.5 : 0.5;
+            toggle_row<N>(p, k, d, cr, ci);
+        }
+        double bs_re = 0.0, bs_im = 0.0;
+        // Every quantity that selects a row or a sign inside the loops is a function of the local step
+        // only (warp-uniform).  The one thread-dependent direction -- the toggle of Gray bit L-1 in
+        // the middle of the chunk, which follows bit 0 of the chunk index -- is first applied with the
+        // even-chunk direction and then corrected for odd chunks (factor 2 or 0, no divergence); the
+        // chunk is swept as two segments so that the correction sits between two loops.
+        const double midfix = (cc & 1ull) ? 2.0 : 0.0;
+        const unsigned int vzero = (unsigned int)(cc >> 63) << 31;  // == 0, see pm_one
+        const unsigned int seg = nsteps >= 4u ? (nsteps >> 1) : nsteps;
+        if (seg >= (unsigned int)U) {
+#pragma unroll 1
+            for (unsigned int s0 = 0; s0 < nsteps; s0 += seg) {
+#pragma unroll 1
+                for (unsigned int s = s0; s < s0 + seg; s += U) {
+                    UnrolledTerms<N, CH, U, 0>::run(p, s, vzero, cr, ci, bs_re, bs_im);
+                    fold_chunk_acc(acc, bs_re, bs_im);
+                    bs_re = 0.0;
+                    bs_im = 0.0;
+                }
+                if (s0 == 0) toggle_row<N>(p, L - 1, midfix, cr, ci);
+            }
+        } else {
+            // short chunks (tiny matrices): one pair of terms per iteration, run-time rows and signs.
+            // (After the last pair b == L <= rows-1 is toggled into column sums never used again.)
+#pragma unroll 1
+            for (unsigned int s0 = 0; s0 < nsteps; s0 += seg) {
+#pragma unroll 1
+                for (unsigned int s = s0; s < s0 + seg; s += 2) {
+                    const double sg1 = pm_one((s >> 1) & 1u, vzero);
+                    const unsigned int s2 = s + 2;
+                    const int b = __ffs(s2) - 1;
+                    const double sg = pm_one((s2 >> (b + 1)) & 1u, vzero);
+                    term_toggle<N, false, 1, true, 2>(p, 0, sg1, cr, ci, bs_re, bs_im);
+                    term_toggle<N, true, 1, false, 2>(p, b, sg, cr, ci, bs_re, bs_im);
+                    fold_chunk_acc(acc, bs_re, bs_im);
+                    bs_re = 0.0;
+                    bs_im = 0.0;
+                }
+                if (s0 == 0 && seg < nsteps) toggle_row<N>(p, L - 1, midfix, cr, ci);
+            }
+        }
+        // chunk sum -> thread total; every group of terms starts with the parity of the chunk's
+        // start code
+        cdd cacc, tot;
+        cacc.re.hi = acc[0 * kPlainThreads];
+        cacc.re.lo = acc[1 * kPlainThreads];
+        cacc.im.hi = acc[2 * kPlainThreads];
+        cacc.im.lo = acc[3 * kPlainThreads];
+        tot.re.hi = acc[4 * kPlainThreads];
+        tot.re.lo = acc[5 * kPlainThreads];
+        tot.im.hi = acc[6 * kPlainThreads];
+        tot.im.lo = acc[7 * kPlainThreads];
+        if (__popcll(gray0) & 1) {
+            cacc.re = dd_neg(cacc.re);
+            cacc.im = dd_neg(cacc.im);
+        }
+        if (!live) cacc = cdd_zero();
+        cdd_add(tot, cacc);
+        acc[0 * kPlainThreads] = 0.0;
+        acc[1 * kPlainThreads] = 0.0;
+        acc[2 * kPlainThreads] = 0.0;
+        acc[3 * kPlainThreads] = 0.0;
+        acc[4 * kPlainThreads] = tot.re.hi;
+        acc[5 * kPlainThreads] = tot.re.lo;
+        acc[6 * kPlainThreads] = tot.im.hi;
+        acc[7 * kPlainThreads] = tot.im.lo;
+    }
+    cdd tot;
+    tot.re.hi = acc[4 * kPlainThreads];
+    tot.re.lo = acc[5 * kPlainThreads];
+    tot.im.hi = acc[6 * kPlainThreads];
+    tot.im.lo = acc[7 * kPlainThreads];
+    grid_reduce_cdd<kPlainThreads>(tot, p.partials, p.counter, p.out, p.phase);
+}
+
+// Rolled form of the same sweep (one pair of terms per loop iteration, accumulators in registers,
+// run-time row for the second toggle).  ptxas schedules this form better than the unrolled one when
+// the column sums alone take ~160 registers (N >= 35); which form serves which N is decided by
+// measurement (tools/microbench/tune_plain.cu -> default_unroll).
+template <int N, int CH = default_chains(N)>
+__global__ void __launch_bounds__(kPlainThreads, 1)
+glynn_plain_rolled_kernel(const __grid_constant__ PlainParams<N> p) {
     const int rows = p.rows;
     const int L = p.L;
     const unsigned int nsteps = 1u << L;
@@ -207,51 +416,43 @@ glynn_plain_kernel(const __grid_constant__ PlainParams<N> p) {
         p.chunk_begin + (unsigned long long)blockIdx.x * kPlainThreads + threadIdx.x;
     for (unsigned int it = 0; it < p.iters; it++, c += nthreads) {
         const bool live = c < p.chunk_end;
-        const unsigned long long g0 = (live ? c : p.chunk_begin) << L;
+        const unsigned long long cc = live ? c : p.chunk_begin;
+        const unsigned long long g0 = cc << L;
         const unsigned long long gray0 = g0 ^ (g0 >> 1);
-        // ---- seed the column sums from the chunk's start code (reference: BBFG...hpp:136-176)
         double cr[N], ci[N];
 #pragma unroll
         for (int j = 0; j < N; j++) {
-            cr[j] = 0.5 * p.A2[0][j].x;
-            ci[j] = 0.5 * p.A2[0][j].y;
+            cr[j] = 0.5 * p.A2[rows - 1][j].x;
+            if (j < N - 1) ci[j] = 0.5 * p.A2[rows - 1][j].y;
         }
 #pragma unroll 1
-        for (int i = 1; i < rows; i++) {
-            const double d = ((gray0 >> (rows - 1 - i)) & 1ull) ? -0.5 : 0.5;
-            toggle_row<N>(p, i, d, cr, ci);
+        for (int k = 0; k < rows - 1; k++) {
+            const double d = ((gray0 >> k) & 1ull) ? -0.5 : 0.5;
+            toggle_row<N>(p, k, d, cr, ci);
         }
         cdd cacc = cdd_zero();
-        const unsigned int g0lo = (unsigned int)g0;
         double bs_re = 0.0, bs_im = 0.0;
+        const double midfix = (cc & 1ull) ? 2.0 : 0.0;  // see glynn_plain_kernel
+        const unsigned int half = nsteps >> 1;
+        const int r0 = p.fast_row;
 #pragma unroll 1
         for (unsigned int s = 0; s < nsteps; s += 2) {
-            // two consecutive terms g, g+1 (g = g0+s even): Gray bit 0 is set going into g+1 iff bit 1
-            // of g is clear (warp-uniform whenever L >= 2)
-            term_acc<N, false, CH>(cr, ci, bs_re, bs_im);
-            toggle_row<N>(p, rows - 1, (((g0lo | s) >> 1) & 1u) ? 1.0 : -1.0, cr, ci);
-            term_acc<N, true, CH>(cr, ci, bs_re, bs_im);
-            if (DDP == 2 || (s & (DDP - 2)) == (DDP - 2)) {
+            const double sg1 = ((s >> 1) & 1u) ? 1.0 : -1.0;
+            const unsigned int s2 = s + 2;
+            const int b = __ffs(s2) - 1;
+            const double sg = ((s2 >> (b + 1)) & 1u) ? 1.0 : -1.0;
+            term_toggle<N, false, CH, true, 2>(p, r0, sg1, cr, ci, bs_re, bs_im);
+            term_toggle<N, true, CH, false, 2>(p, r0 + b, sg, cr, ci, bs_re, bs_im);
+            if (s2 == half) toggle_row<N>(p, L - 1, midfix, cr, ci);
+            if ((s & 6u) == 6u) {
                 dd_add_d(cacc.re, bs_re);
                 dd_add_d(cacc.im, bs_im);
                 bs_re = 0.0;
                 bs_im = 0.0;
             }
-            // ---- general toggle into term g+2: Gray bit b = ctz(s+2) >= 1, warp-uniform row, per-thread
-            // sign (it depends on the chunk index only for b == L-1).  Unconditional so that the loop
-            // body is one basic block: after the last pair b == L and row rows-1-L >= 0 is toggled
-            // into column sums that are never used again.
-            const unsigned int s2 = s + 2;
-            const int b = __ffs(s2) - 1;
-            const unsigned long long g = g0 + s2;
-            const double sg = (((g >> b) ^ (g >> (b + 1))) & 1ull) ? -1.0 : 1.0;
-            toggle_row<N>(p, rows - 1 - b, sg, cr, ci);
         }
-        if (DDP > 2) {  // leftover when the chunk is shorter than DDP terms (bs is zero otherwise)
-            dd_add_d(cacc.re, bs_re);
-            dd_add_d(cacc.im, bs_im);
-        }
-        // every group of terms starts with the parity of the chunk's start code
+        dd_add_d(cacc.re, bs_re);  // leftover of chunks shorter than 8 terms (zero otherwise)
+        dd_add_d(cacc.im, bs_im);
         if (__popcll(gray0) & 1) {
             cacc.re = dd_neg(cacc.re);
             cacc.im = dd_neg(cacc.im);
@@ -259,7 +460,7 @@ glynn_plain_kernel(const __grid_constant__ PlainParams<N> p) {
         if (!live) cacc = cdd_zero();
         cdd_add(tot, cacc);
     }
-    grid_reduce_cdd<kPlainThreads>(tot, p.partials, p.counter, p.out);
+    grid_reduce_cdd<kPlainThreads>(tot, p.partials, p.counter, p.out, p.phase);
 }
 
 }  // namespace pqb200

@@ -3,6 +3,7 @@
 // instantiations build in parallel.
 #include "glynn_plain.cuh"
 #include "launch.h"
+#include "plain_host.h"
 
 #ifndef PQB_NLO
 #error "define PQB_NLO and PQB_NHI"
@@ -15,17 +16,8 @@ static cudaError_t launch_plain_n(const PlainLaunchArgs& x) {
     static_assert(sizeof(PlainParams<N>) <= 32764, "kernel parameter space exceeded");
     PlainParams<N> p;
     const int rows = (int)x.rows, cols = (int)x.cols;
-    for (int i = 0; i < N; i++)
-        for (int j = 0; j < N; j++) {
-            double2 v = make_double2(0.0, 0.0);
-            if (i < rows && j < cols) {
-                v.x = 2.0 * x.a[2 * (i * x.stride + j)];
-                v.y = 2.0 * x.a[2 * (i * x.stride + j) + 1];
-            } else if (i == 0 && j >= cols) {
-                v.x = 2.0;  // padding column: column sum is the constant 1 (row 0 has delta = +1)
-            }
-            p.A2[i][j] = v;
-        }
+    static_assert(sizeof(p.A2) == sizeof(double) * 2 * N * N, "A2 layout");
+    plain_normalise(x.a, rows, cols, x.stride, N, reinterpret_cast<double*>(&p.A2[0][0]), p.phase);
     p.rows = rows;
     p.L = x.L;
     p.chunk_begin = x.chunk_begin;
@@ -35,15 +27,22 @@ static cudaError_t launch_plain_n(const PlainLaunchArgs& x) {
     p.partials = x.partials;
     p.counter = x.counter;
     p.out = x.out;
-    glynn_plain_kernel<N><<<x.grid, kPlainThreads, 0, x.stream>>>(p);
+    p.fast_row = 0;
+    if constexpr (default_unroll(N) == 2)
+        glynn_plain_rolled_kernel<N><<<x.grid, kPlainThreads, 0, x.stream>>>(p);
+    else
+        glynn_plain_kernel<N><<<x.grid, kPlainThreads, 0, x.stream>>>(p);
     return cudaGetLastError();
 }
 
 template <int N>
 static int occupancy_plain_n(void) {
     int nb = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, glynn_plain_kernel<N>,
-                                                                  kPlainThreads, 0);
+    cudaError_t e;
+    if constexpr (default_unroll(N) == 2)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, glynn_plain_rolled_kernel<N>, kPlainThreads, 0);
+    else
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, glynn_plain_kernel<N>, kPlainThreads, 0);
     return e == cudaSuccess ? nb : -1;
 }
 

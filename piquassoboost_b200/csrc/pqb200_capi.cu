@@ -20,6 +20,7 @@
 #include "../../include/pqb200.h"
 #include "dd.cuh"
 #include "launch.h"
+#include "plain_host.h"
 #include "batch_host.h"
 #include "laplace_host.h"
 #include "svd_host.h"
@@ -45,6 +46,12 @@ PQB_DECL_REP_FILL(31)
 PQB_DECL_REP_FILL(36)
 PQB_DECL_REP_FILL(40)
 PQB_DECL_REP_FILL(43)
+
+namespace pqb200 {
+cudaError_t launch_plain_dd(const double* d_a, int n, int L, unsigned long long cb, unsigned long long ce,
+                            int grid, double* partials, unsigned int* counter, double* out,
+                            cudaStream_t stream);
+}
 
 namespace {
 
@@ -213,11 +220,14 @@ struct PlainPlan {
 // Choose the chunk length: minimise  waves * (seed cost + 2^L * step cost)  for the busiest device.
 PlainPlan plan_plain(int rows, int cols, int max_resident_threads, unsigned long long shards) {
     PlainPlan pl;
-    pl.N = std::max(rows, cols);
+    pl.N = plain_kernel_cols(rows, cols);
     const int lmax = std::min(rows - 1, kMaxChunkLog);
     double best = 1e300;
     pl.L = lmax;
-    for (int L = 1; L <= lmax; L++) {
+    // L == 1 only for rows == 2 (a single chunk): the kernel derives every toggle direction from the
+    // local step, which needs L >= 2 as soon as there is more than one chunk
+    const int lmin = std::min(2, lmax);
+    for (int L = lmin; L <= lmax; L++) {
         const unsigned long long C = 1ull << (rows - 1 - L);
         const unsigned long long per_shard = (C + shards - 1) / shards;
         const unsigned long long threads =
@@ -232,7 +242,7 @@ PlainPlan plan_plain(int rows, int cols, int max_resident_threads, unsigned long
     }
     if (const char* f = getenv("PQB200_FORCE_L")) {  // tuning / debugging aid
         const int L = atoi(f);
-        if (L >= 1 && L <= rows - 1) pl.L = L;
+        if (L >= lmin && L <= rows - 1) pl.L = L;
     }
     pl.nchunks = 1ull << (rows - 1 - pl.L);
     return pl;
@@ -278,7 +288,8 @@ int launch_plain_range(DeviceCtx& c, const double* a, size_t rows, size_t cols, 
 int check_plain_args(const double* a, size_t rows, size_t cols, size_t stride) {
     if (!a) return fail(PQB200_ERR_ARG, "matrix pointer is null");
     if (stride < cols) return fail(PQB200_ERR_ARG, "stride is smaller than the number of columns");
-    if (std::max(rows, cols) > (size_t)kMaxPlainN)
+    if (std::max(rows, cols) > (size_t)kMaxPlainN ||
+        (rows >= 2 && rows <= cols + 1 && plain_kernel_cols((int)rows, (int)cols) > kMaxPlainN))
         return fail(PQB200_ERR_ARG, "matrix dimension exceeds 45 (kernel-parameter resident matrix limit of this build)");
     return PQB200_OK;
 }
@@ -435,6 +446,69 @@ int pqb200_permanent(const double* a, size_t rows, size_t cols, size_t stride, i
     g_stats = {0.0, 0.0, 0, used};
     if (plain_edge_case(a, rows, cols, stride, out)) return PQB200_OK;
     return plain_multi_device(a, rows, cols, stride, used, rows, out);
+}
+
+int pqb200_permanent_dd(const double* a, size_t rows, size_t cols, size_t stride, int ndev,
+                        double out_dd[4]) {
+    if (!out_dd) return fail(PQB200_ERR_ARG, "output pointer is null");
+    int rc = check_plain_args(a, rows, cols, stride);
+    if (rc) return rc;
+    if (rows != cols || rows < 2)
+        return fail(PQB200_ERR_ARG, "the double-double evaluation takes a square matrix with n >= 2");
+    std::lock_guard<std::mutex> lk(g_mu);
+    int used = 0;
+    rc = ensure_devices(ndev, &used);
+    if (rc) return rc;
+    const int n = (int)rows;
+    const int L = std::min(n - 1, kMaxChunkLog);
+    const unsigned long long nchunks = 1ull << (n - 1 - L);
+    if ((unsigned long long)used > nchunks) used = (int)nchunks;
+    std::vector<double> dense(2 * (size_t)n * n);
+    for (int i = 0; i < n; i++) memcpy(&dense[2 * (size_t)i * n], a + 2 * i * stride, 16 * (size_t)n);
+    std::vector<double*> d_a((size_t)used, nullptr);
+    std::vector<double> parts(4 * (size_t)used);
+    g_stats = {0.0, ldexp(1.0, n - 1), (uint64_t)used, used};
+    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
+    CUDA_TRY(cudaEventRecord(g_devs[0].e0, g_devs[0].stream));
+    for (int d = 0; d < used; d++) {
+        DeviceCtx& c = g_devs[d];
+        CUDA_TRY(cudaSetDevice(c.dev));
+        CUDA_TRY(cudaMalloc(&d_a[d], 16 * (size_t)n * n));
+        CUDA_TRY(cudaMemcpyAsync(d_a[d], dense.data(), 16 * (size_t)n * n, cudaMemcpyHostToDevice, c.stream));
+        const unsigned long long cb = nchunks * (unsigned long long)d / (unsigned long long)used;
+        const unsigned long long ce = nchunks * (unsigned long long)(d + 1) / (unsigned long long)used;
+        const unsigned long long want = (ce - cb + kPlainThreads - 1) / kPlainThreads;
+        const int grid = (int)std::min<unsigned long long>(want, (unsigned long long)c.sm_count);
+        CUDA_TRY(launch_plain_dd(d_a[d], n, L, cb, ce, grid, c.partials, c.counter, c.d_out, c.stream));
+        CUDA_TRY(cudaMemcpyAsync(c.h_out, c.d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        if (d == 0) CUDA_TRY(cudaEventRecord(c.e1, c.stream));
+    }
+    for (int d = 0; d < used; d++) {
+        DeviceCtx& c = g_devs[d];
+        CUDA_TRY(cudaSetDevice(c.dev));
+        CUDA_TRY(cudaStreamSynchronize(c.stream));
+        memcpy(&parts[4 * (size_t)d], c.h_out, 4 * sizeof(double));
+        CUDA_TRY(cudaFree(d_a[d]));
+    }
+    float ms = 0.f;
+    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
+    CUDA_TRY(cudaEventElapsedTime(&ms, g_devs[0].e0, g_devs[0].e1));
+    g_stats.kernel_ms = ms;
+    cdd tot = cdd_zero();
+    for (int d = 0; d < used; d++) {
+        cdd x;
+        x.re.hi = parts[4 * d + 0];
+        x.re.lo = parts[4 * d + 1];
+        x.im.hi = parts[4 * d + 2];
+        x.im.lo = parts[4 * d + 3];
+        cdd_add(tot, x);
+    }
+    const int e = -(n - 1);  // exact power-of-two scaling of both parts
+    out_dd[0] = ldexp(tot.re.hi, e);
+    out_dd[1] = ldexp(tot.re.lo, e);
+    out_dd[2] = ldexp(tot.im.hi, e);
+    out_dd[3] = ldexp(tot.im.lo, e);
+    return PQB200_OK;
 }
 
 // one repeated-row permanent over `used` devices; caller holds g_mu

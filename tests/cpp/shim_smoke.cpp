@@ -29,6 +29,24 @@ int main() {
         auto w = pqb200::GlynnPermanentCalculator().calculate(m);
         std::printf("repeated=(%.15g,%.15g) plain=(%.15g,%.15g)\n", v.real(), v.imag(), w.real(), w.imag());
         if (std::abs(v - std::complex<double>(-1, 0)) > 1e-14) return 2;
+        // BatchednPermanentCalculator: two state pairs against the same interferometer
+        State in2{{1, 1}}, out2{{1, 1}};
+        pqb200::BatchednPermanentCalculator<Mat, State> batch(m);
+        batch.reserve_space(2);
+        batch.add(&in, &out, 0);
+        batch.add(&in2, &out2, 1);
+        auto b = batch.calculate();
+        std::printf("batch=(%.15g,%.15g) (%.15g,%.15g)\n", b[0].real(), b[0].imag(), b[1].real(), b[1].imag());
+        if (std::abs(b[0] - v) > 1e-14 || std::abs(b[1] - w) > 1e-14) return 3;
+        bool threw = false;
+        try {
+            State bad{{1, 0}};
+            batch.reserve_space(1);
+            batch.add(&bad, &out, 0);
+        } catch (std::string&) {
+            threw = true;
+        }
+        if (!threw) return 4;
         return 0;
     } catch (std::string& e) {
         std::printf("threw std::string: %s\n", e.c_str());

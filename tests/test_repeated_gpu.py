@@ -109,3 +109,16 @@ def test_free_functions(pqb, ref):
     want = ref.bbfg_repeated(U, a, b, True)
     assert relerr(pqb.permanent_CPU_repeated_double(U, a, b), want) < TOL
     assert relerr(pqb.permanent_CPU_repeated_long_double(U, a, b), want) < TOL
+
+
+def test_connector_permanent_hook(pqb, ref):
+    """piquassoboost/connector.py:23-31: the callable installed as BoostConnector.permanent."""
+    from piquassoboost_b200 import connector
+    U = haar_unitary(6, 31)
+    a, b = np.array([1, 0, 2, 0, 1, 0]), np.array([0, 1, 1, 1, 0, 1])
+    assert relerr(connector.cpp_permanent_function(U, a, b), ref.bbfg_repeated(U, a, b, True)) < TOL
+    # list-valued states give a list, which the reference hook maps to 1.0 (connector.py:27-29)
+    assert connector.cpp_permanent_function(U, [a], [b]) == 1.0
+    res = connector.permanent_function_batch(U, [a, [2, 2, 0, 0, 0, 0]], [b])
+    assert relerr(res[0][0], ref.bbfg_repeated(U, a, b, True)) < TOL
+    assert relerr(res[1][0], ref.bbfg_repeated(U, [2, 2, 0, 0, 0, 0], b, True)) < TOL

@@ -58,11 +58,11 @@ void run_rate(const char* name, int iters) {
            instr / ms / 1e9, mhz, instr / (ms * 1e-3) / 148 / (mhz * 1e6));
 }
 
-template <int N, int DDP, int CH>
+template <int N, int CH, int U>
 void run_variant(const std::vector<std::complex<double>>& A, int n, int L, unsigned long long nchunks, double* partials, unsigned int* counter, double* out) {
     static PlainParams<N> p;
     for (int i = 0; i < n; i++) for (int j = 0; j < N; j++) p.A2[i][j] = make_double2(2 * A[i * N + j].real(), 2 * A[i * N + j].imag());
-    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, glynn_plain_kernel<N, DDP, CH>, 256, 0));
+    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, glynn_plain_kernel<N, CH, U>, 256, 0));
     int grid = 148 * occ;
     p.rows = n; p.L = L; p.chunk_begin = 0; p.chunk_end = nchunks;
     p.iters = (unsigned)((nchunks + (unsigned long long)grid * 256 - 1) / ((unsigned long long)grid * 256));
@@ -71,15 +71,15 @@ void run_variant(const std::vector<std::complex<double>>& A, int n, int L, unsig
     float best = 1e30f;
     for (int rep = 0; rep < 3; rep++) {
         cudaEventRecord(e0);
-        glynn_plain_kernel<N, DDP, CH><<<grid, 256>>>(p);
+        glynn_plain_kernel<N, CH, U><<<grid, 256>>>(p);
         cudaEventRecord(e1); CK(cudaDeviceSynchronize());
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (rep) best = std::min(best, ms);
     }
     double h[4]; CK(cudaMemcpy(h, out, 32, cudaMemcpyDeviceToHost));
-    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, glynn_plain_kernel<N, DDP, CH>));
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, glynn_plain_kernel<N, CH, U>));
     const double steps = (double)nchunks * (double)(1ull << L);
-    printf("VAR N=%d DDP=%d CH=%d L=%d regs=%d local=%zu occ=%d: %.3f ms  %.4e steps/s  %.2f TFLOP/s  sum=(%.12e,%.12e)\n", N, DDP, CH, L,
+    printf("VAR N=%d CH=%d U=%d L=%d regs=%d local=%zu occ=%d: %.3f ms  %.4e steps/s  %.2f TFLOP/s  sum=(%.12e,%.12e)\n", N, CH, U, L,
            fa.numRegs, fa.localSizeBytes, occ, best, steps / (best * 1e-3), steps * 8 * N / best / 1e9, h[0] + h[1], h[2] + h[3]);
 }
 
@@ -92,23 +92,20 @@ void sweep(int L, unsigned long long nchunks) {
     double* partials; unsigned int* counter; double* out;
     CK(cudaMalloc(&partials, 4 * 8 * 4096)); CK(cudaMalloc(&counter, 4)); CK(cudaMemset(counter, 0, 4)); CK(cudaMalloc(&out, 32));
     run_variant<N, 2, 4>(A, n, L, nchunks, partials, counter, out);
+    run_variant<N, 4, 4>(A, n, L, nchunks, partials, counter, out);
     run_variant<N, 8, 4>(A, n, L, nchunks, partials, counter, out);
-    run_variant<N, 32, 4>(A, n, L, nchunks, partials, counter, out);
-    run_variant<N, 8, 2>(A, n, L, nchunks, partials, counter, out);
-    run_variant<N, 8, 3>(A, n, L, nchunks, partials, counter, out);
-    run_variant<N, 8, 6>(A, n, L, nchunks, partials, counter, out);
+    run_variant<N, 2, 8>(A, n, L, nchunks, partials, counter, out);
+    run_variant<N, 4, 8>(A, n, L, nchunks, partials, counter, out);
     run_variant<N, 8, 8>(A, n, L, nchunks, partials, counter, out);
     cudaFree(partials); cudaFree(counter); cudaFree(out);
 }
 
 int main() {
     run_rate<0, 1>("DFMA R,UR,UR", 40000); run_rate<0, 3>("DFMA R,R,R", 40000);
-    run_rate<1, 1>("DADD R,UR", 40000); run_rate<1, 3>("DADD R,R", 40000);
-    run_rate<2, 1>("DMUL R,UR", 40000); run_rate<2, 3>("DMUL R,R", 40000);
-    run_rate<3, 3>("DMUL/DFMA mix", 40000);
-    run_rate<0, 3>("DFMA R,R,R long", 400000);
     sweep<40>(12, 1ull << 19);
-    sweep<30>(12, 1ull << 19);
-    sweep<20>(12, 1ull << 19);
+    sweep<38>(12, 1ull << 19);
+    sweep<36>(12, 1ull << 19);
+    sweep<34>(12, 1ull << 19);
+    sweep<32>(12, 1ull << 19);
     return 0;
 }
