@@ -244,6 +244,17 @@ def run_b200(args, rank, local_rank, world):
         got = pqb.GlynnPermanent(B).calculate()
         want = refbind.bbfg(B, True) if refbind.available() else oraclebind.bbfg(B, oraclebind.LONG_DOUBLE)
         cpu_equiv, cpu_desc, _ = cpu_reference_rate(n, args.cpu_seconds)
+        # the value of THIS run's permanent against the committed double-double evaluation (itself
+        # pinned to the reference's long double up to n=36; tests/golden/plain_dd_reference.json)
+        accuracy = None
+        try:
+            gold = json.load(open(os.path.join(ROOT, "tests", "golden", "plain_dd_reference.json")))["cases"]
+            if str(n) in gold:
+                g = complex(*[float.fromhex(x) for x in gold[str(n)]["dd_parts_hex"]][0::2])
+                accuracy = {"rel_err_vs_double_double_golden": abs(value_perm - g) / abs(g),
+                            "tolerance": 1e-10, "golden": "tests/golden/plain_dd_reference.json"}
+        except OSError:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -263,7 +274,10 @@ def run_b200(args, rank, local_rank, world):
                                         f"(DADD-only issue rate {dadd.value / 1e12:.2f} T thread-instr/s; "
                                         "nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2)",
                          "algorithmic_flops_per_step": 8 * n, "kernel_ms": kernel_ms,
-                         "instruction_mix_ceiling": (8.0 * n) / (2.0 * (6 * n - 4))},
+                         # FP64 instructions per Gray step after the real-row/real-column normalisation:
+                         # 5.5n - 6.5; each issues at most 1 FMA = 2 flop
+                         "instruction_mix_ceiling": (8.0 * n) / (2.0 * (5.5 * n - 6.5))},
+            "accuracy": accuracy,
             "cpu_baseline": cpu_desc,
             "e2e": {"value": steps_per_perm * args.steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": 16 * n * n * world, "d2h_bytes_per_step": 32 * world,

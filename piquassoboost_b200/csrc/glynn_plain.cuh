@@ -45,6 +45,8 @@ struct PlainParams {
     double2 A2[N][N];  // 2*a[i][j] (exact doubling), rows x N used
     int rows;          // n, 2 <= rows <= N
     int L;             // log2(chunk length), 1 <= L <= rows-1
+    int K;             // log2(sub-chunk length), 1 <= K <= L: the column sums are re-derived from a
+                       // per-thread anchor (shared memory) every 2^K steps
     unsigned long long chunk_begin, chunk_end;  // this launch's (this GPU's) chunk range
     unsigned int iters;                         // ceil((chunk_end-chunk_begin) / (gridDim.x*256))
     double* partials;                           // [gridDim.x][4]
@@ -172,12 +174,13 @@ __device__ __forceinline__ void cmul(double& xr, double& xi, double yr, double y
 //   unroll 2   : rolled kernel (glynn_plain_rolled_kernel), best when the column sums alone take
 //                >= 136 registers;   unroll 4 / 8 : terms per iteration of glynn_plain_kernel.
 __host__ __device__ constexpr int default_unroll(int n) {
-    return n >= 34 ? 2 : (n >= 17 && n <= 22) ? 4 : 8;
+    return n == 32 ? 8 : n >= 27 ? 2 : (n >= 17 && n <= 22) ? 4 : 8;
 }
 __host__ __device__ constexpr int default_chains(int n) {
-    return n >= 45 ? 2 : n == 44 ? 4 : n == 43 ? 6 : n == 42 ? 3 : n == 41 ? 8 : n == 40 ? 4 : n == 39 ? 3
-         : n == 38 ? 4 : n == 37 ? 8 : n == 36 ? 6 : n == 35 ? 2 : n == 34 ? 8 : n == 33 ? 4 : n == 32 ? 8
-         : n == 31 ? 4 : n == 30 ? 2 : n == 29 ? 8 : n >= 23 ? 4 : n >= 17 ? 2 : n >= 8 ? 4 : n >= 4 ? 2 : 1;
+    return n >= 45 ? 2 : n == 44 ? 4 : n == 43 ? 4 : n == 42 ? 2 : n == 41 ? 4 : n == 40 ? 4 : n == 39 ? 2
+         : n == 38 ? 4 : n == 37 ? 8 : n == 36 ? 8 : n == 35 ? 4 : n == 34 ? 6 : n == 33 ? 6 : n == 32 ? 4
+         : n == 31 ? 6 : n == 30 ? 8 : n == 29 ? 6 : n == 28 ? 8 : n == 27 ? 8 : n == 26 ? 2 : n == 25 ? 2
+         : n == 24 ? 8 : n == 23 ? 4 : n >= 17 ? 2 : n >= 8 ? 4 : n >= 4 ? 2 : 1;
 }
 
 // column update  x <- x + sign * a   with  SIGNMODE 0: sign = +1 and 1: sign = -1 at compile time (DADD
@@ -290,31 +293,58 @@ struct UnrolledTerms {
     }
 };
 
-// CH: independent multiply chains per term; U: terms per iteration of the unrolled chunk loop (the
-// partial sum is folded into the double-double accumulator once per iteration).
-template <int N, int CH = default_chains(N), int U = default_unroll(N)>
-__global__ void __launch_bounds__(kPlainThreads, 1)
-glynn_plain_kernel(const __grid_constant__ PlainParams<N> p) {
-    const int rows = p.rows;
-    const int L = p.L;
-    const unsigned int nsteps = 1u << L;
-    const unsigned long long nthreads = (unsigned long long)gridDim.x * kPlainThreads;
-    // The double-double accumulators are touched once per U terms (chunk sum) / once per chunk
-    // (thread total): they live in shared memory, not in the register file the column sums need.
-    __shared__ double s_acc[8][kPlainThreads];
-    double* const acc = &s_acc[0][threadIdx.x];
+// ---- two-level re-seeding --------------------------------------------------------------------------
+// Rounding drift of the running column sums grows with the number of in-place updates since they were
+// last derived from exact data (measured: it, not the FP64 products, dominates the error of the
+// result; profiles/accuracy_*_r1.jsonl).  A chunk of 2^L steps is therefore swept as 2^(L-K)
+// sub-chunks: the thread keeps an ANCHOR = column sums at the sub-chunk start in shared memory
+// ((2N-1) doubles per thread, stride kPlainThreads: conflict-free), which only ever receives the
+// single high-row toggle between consecutive sub-chunks (Gray code of the sub-chunk index), and the
+// working sums are re-derived from it every 2^K steps:
+//     c_start(sc) = anchor(sc)  -  (sc odd ? 2 a_{K-1} : 0)        (Gray bit K-1 follows bit 0 of sc)
+// so that no column sum is ever more than 2^(L-K) + 2^K + 2 roundings away from a full seed, at the
+// cost of (2N-1) LDS + STS and 2(2N-1) DFMA per 2^K steps (~1 %).
+extern __shared__ double s_anchor[];
+
+template <int N>
+__device__ __forceinline__ void anchor_store(double* anc, const double (&cr)[N], const double (&ci)[N]) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc[k * kPlainThreads] = 0.0;
-    unsigned long long c =
-        p.chunk_begin + (unsigned long long)blockIdx.x * kPlainThreads + threadIdx.x;
-    for (unsigned int it = 0; it < p.iters; it++, c += nthreads) {
-        const bool live = c < p.chunk_end;
-        const unsigned long long cc = live ? c : p.chunk_begin;
-        const unsigned long long g0 = cc << L;
+    for (int j = 0; j < N; j++) {
+        anc[(2 * j) * kPlainThreads] = cr[j];
+        if (j < N - 1) anc[(2 * j + 1) * kPlainThreads] = ci[j];
+    }
+}
+
+// anchor += sg * A2[row];  c = anchor + fix * A2[fixrow]
+template <int N>
+__device__ __forceinline__ void anchor_step(const PlainParams<N>& p, double* anc, int row, double sg,
+                                            int fixrow, double fix, double (&cr)[N], double (&ci)[N]) {
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        double x = anc[(2 * j) * kPlainThreads];
+        x = fma(sg, p.A2[row][j].x, x);
+        anc[(2 * j) * kPlainThreads] = x;
+        cr[j] = fma(fix, p.A2[fixrow][j].x, x);
+        if (j < N - 1) {
+            double y = anc[(2 * j + 1) * kPlainThreads];
+            y = fma(sg, p.A2[row][j].y, y);
+            anc[(2 * j + 1) * kPlainThreads] = y;
+            ci[j] = fma(fix, p.A2[fixrow][j].y, y);
+        }
+    }
+}
+
+// Start of sub-chunk t of a chunk whose first sub-chunk index is sc0: full seed for t == 0
+// (reference: BBFGPermanentCalculator.hpp:136-176), anchor step otherwise.
+// Row order in A2: index k < rows-1 is the row of Gray bit k, index rows-1 the delta=+1 row.
+template <int N>
+__device__ __forceinline__ void subchunk_start(const PlainParams<N>& p, double* anc, unsigned int t,
+                                               unsigned int nsub, unsigned long long sc, int K,
+                                               double (&cr)[N], double (&ci)[N]) {
+    if (t == 0) {
+        const int rows = p.rows;
+        const unsigned long long g0 = sc << K;
         const unsigned long long gray0 = g0 ^ (g0 >> 1);
-        // ---- seed the column sums from the chunk's start code (reference: BBFG...hpp:136-176).
-        // Row order in A2: index k < rows-1 is the row of Gray bit k, index rows-1 the delta=+1 row.
-        double cr[N], ci[N];
 #pragma unroll
         for (int j = 0; j < N; j++) {
             cr[j] = 0.5 * p.A2[rows - 1][j].x;
@@ -325,10 +355,47 @@ glynn_plain_kernel(const __grid_constant__ PlainParams<N> p) {
             const double d = ((gray0 >> k) & 1ull) ? -0.5 : 0.5;
             toggle_row<N>(p, k, d, cr, ci);
         }
+        if (nsub > 1) anchor_store<N>(anc, cr, ci);
+    } else {
+        // Gray bit K+b of the step index (bit b of the sub-chunk index's Gray code), b = ctz(t), becomes
+        // set iff bit b+1 of sc is clear
+        const int b = __ffs(t) - 1;
+        const double sg = ((sc >> (b + 1)) & 1ull) ? 1.0 : -1.0;
+        anchor_step<N>(p, anc, K + b, sg, K - 1, (sc & 1ull) ? -1.0 : 0.0, cr, ci);
+    }
+}
+
+// CH: independent multiply chains per term; U: terms per iteration of the unrolled chunk loop (the
+// partial sum is folded into the double-double accumulator once per iteration).
+template <int N, int CH = default_chains(N), int U = default_unroll(N)>
+__global__ void __launch_bounds__(kPlainThreads, 1)
+glynn_plain_kernel(const __grid_constant__ PlainParams<N> p) {
+    const int L = p.L, K = p.K;
+    const unsigned int nsteps = 1u << K;        // steps per sub-chunk
+    const unsigned int nsub = 1u << (L - K);    // sub-chunks per chunk
+    const unsigned long long nthreads = (unsigned long long)gridDim.x * kPlainThreads;
+    double* const anc = s_anchor + threadIdx.x;
+    // The double-double accumulators are touched once per U terms (chunk sum) / once per chunk
+    // (thread total): they live in shared memory, not in the register file the column sums need.
+    __shared__ double s_acc[8][kPlainThreads];
+    double* const acc = &s_acc[0][threadIdx.x];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k * kPlainThreads] = 0.0;
+    unsigned long long c =
+        p.chunk_begin + (unsigned long long)blockIdx.x * kPlainThreads + threadIdx.x;
+    double cr[N], ci[N];
+    for (unsigned int it = 0; it < p.iters; it++, c += nthreads) {
+      const bool live = c < p.chunk_end;
+      const unsigned long long sc0 = (live ? c : p.chunk_begin) << (L - K);
+#pragma unroll 1
+      for (unsigned int t = 0; t < nsub; t++) {
+        const unsigned long long cc = sc0 + t;  // sub-chunk index
+        subchunk_start<N>(p, anc, t, nsub, cc, K, cr, ci);
+        const unsigned long long gray0 = (cc << K) ^ ((cc << K) >> 1);
         double bs_re = 0.0, bs_im = 0.0;
         // Every quantity that selects a row or a sign inside the loops is a function of the local step
-        // only (warp-uniform).  The one thread-dependent direction -- the toggle of Gray bit L-1 in
-        // the middle of the chunk, which follows bit 0 of the chunk index -- is first applied with the
+        // only (warp-uniform).  The one thread-dependent direction -- the toggle of Gray bit K-1 in
+        // the middle of the sub-chunk, which follows bit 0 of the sub-chunk index -- is first applied with the
         // even-chunk direction and then corrected for odd chunks (factor 2 or 0, no divergence); the
         // chunk is swept as two segments so that the correction sits between two loops.
         const double midfix = (cc & 1ull) ? 2.0 : 0.0;
@@ -344,7 +411,7 @@ glynn_plain_kernel(const __grid_constant__ PlainParams<N> p) {
                     bs_re = 0.0;
                     bs_im = 0.0;
                 }
-                if (s0 == 0) toggle_row<N>(p, L - 1, midfix, cr, ci);
+                if (s0 == 0) toggle_row<N>(p, K - 1, midfix, cr, ci);
             }
         } else {
             // short chunks (tiny matrices): one pair of terms per iteration, run-time rows and signs.
@@ -363,7 +430,7 @@ glynn_plain_kernel(const __grid_constant__ PlainParams<N> p) {
                     bs_re = 0.0;
                     bs_im = 0.0;
                 }
-                if (s0 == 0 && seg < nsteps) toggle_row<N>(p, L - 1, midfix, cr, ci);
+                if (s0 == 0 && seg < nsteps) toggle_row<N>(p, K - 1, midfix, cr, ci);
             }
         }
         // chunk sum -> thread total; every group of terms starts with the parity of the chunk's
@@ -391,6 +458,7 @@ glynn_plain_kernel(const __grid_constant__ PlainParams<N> p) {
         acc[5 * kPlainThreads] = tot.re.lo;
         acc[6 * kPlainThreads] = tot.im.hi;
         acc[7 * kPlainThreads] = tot.im.lo;
+      }
     }
     cdd tot;
     tot.re.hi = acc[4 * kPlainThreads];
@@ -407,29 +475,23 @@ glynn_plain_kernel(const __grid_constant__ PlainParams<N> p) {
 template <int N, int CH = default_chains(N)>
 __global__ void __launch_bounds__(kPlainThreads, 1)
 glynn_plain_rolled_kernel(const __grid_constant__ PlainParams<N> p) {
-    const int rows = p.rows;
-    const int L = p.L;
-    const unsigned int nsteps = 1u << L;
+    const int L = p.L, K = p.K;
+    const unsigned int nsteps = 1u << K;        // steps per sub-chunk
+    const unsigned int nsub = 1u << (L - K);    // sub-chunks per chunk
     const unsigned long long nthreads = (unsigned long long)gridDim.x * kPlainThreads;
+    double* const anc = s_anchor + threadIdx.x;
     cdd tot = cdd_zero();
     unsigned long long c =
         p.chunk_begin + (unsigned long long)blockIdx.x * kPlainThreads + threadIdx.x;
+    double cr[N], ci[N];
     for (unsigned int it = 0; it < p.iters; it++, c += nthreads) {
-        const bool live = c < p.chunk_end;
-        const unsigned long long cc = live ? c : p.chunk_begin;
-        const unsigned long long g0 = cc << L;
-        const unsigned long long gray0 = g0 ^ (g0 >> 1);
-        double cr[N], ci[N];
-#pragma unroll
-        for (int j = 0; j < N; j++) {
-            cr[j] = 0.5 * p.A2[rows - 1][j].x;
-            if (j < N - 1) ci[j] = 0.5 * p.A2[rows - 1][j].y;
-        }
+      const bool live = c < p.chunk_end;
+      const unsigned long long sc0 = (live ? c : p.chunk_begin) << (L - K);
 #pragma unroll 1
-        for (int k = 0; k < rows - 1; k++) {
-            const double d = ((gray0 >> k) & 1ull) ? -0.5 : 0.5;
-            toggle_row<N>(p, k, d, cr, ci);
-        }
+      for (unsigned int t = 0; t < nsub; t++) {
+        const unsigned long long cc = sc0 + t;  // sub-chunk index
+        subchunk_start<N>(p, anc, t, nsub, cc, K, cr, ci);
+        const unsigned long long gray0 = (cc << K) ^ ((cc << K) >> 1);
         cdd cacc = cdd_zero();
         double bs_re = 0.0, bs_im = 0.0;
         const double midfix = (cc & 1ull) ? 2.0 : 0.0;  // see glynn_plain_kernel
@@ -443,7 +505,7 @@ glynn_plain_rolled_kernel(const __grid_constant__ PlainParams<N> p) {
             const double sg = ((s2 >> (b + 1)) & 1u) ? 1.0 : -1.0;
             term_toggle<N, false, CH, true, 2>(p, r0, sg1, cr, ci, bs_re, bs_im);
             term_toggle<N, true, CH, false, 2>(p, r0 + b, sg, cr, ci, bs_re, bs_im);
-            if (s2 == half) toggle_row<N>(p, L - 1, midfix, cr, ci);
+            if (s2 == half) toggle_row<N>(p, K - 1, midfix, cr, ci);
             if ((s & 6u) == 6u) {
                 dd_add_d(cacc.re, bs_re);
                 dd_add_d(cacc.im, bs_im);
@@ -459,8 +521,15 @@ glynn_plain_rolled_kernel(const __grid_constant__ PlainParams<N> p) {
         }
         if (!live) cacc = cdd_zero();
         cdd_add(tot, cacc);
+      }
     }
     grid_reduce_cdd<kPlainThreads>(tot, p.partials, p.counter, p.out, p.phase);
+}
+
+// dynamic shared memory of both kernels: the per-thread anchors
+template <int N>
+constexpr size_t plain_anchor_bytes() {
+    return sizeof(double) * (size_t)(2 * N - 1) * kPlainThreads;
 }
 
 }  // namespace pqb200

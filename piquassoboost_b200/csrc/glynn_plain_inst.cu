@@ -12,14 +12,36 @@
 namespace pqb200 {
 
 template <int N>
+static auto plain_kernel_fn() {
+    if constexpr (default_unroll(N) == 2)
+        return &glynn_plain_rolled_kernel<N>;
+    else
+        return &glynn_plain_kernel<N>;
+}
+
+template <int N>
 static cudaError_t launch_plain_n(const PlainLaunchArgs& x) {
     static_assert(sizeof(PlainParams<N>) <= 32764, "kernel parameter space exceeded");
+    static_assert(plain_anchor_bytes<N>() + 8 * kPlainThreads * sizeof(double) + 1024 <= 227 * 1024,
+                  "anchors do not fit the shared memory of one SM");
+    // opt in to the large dynamic shared memory once per device (the attribute is per context)
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        e = cudaFuncSetAttribute(plain_kernel_fn<N>(), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)plain_anchor_bytes<N>());
+        if (e != cudaSuccess) return e;
+        attr_set[dev] = true;
+    }
     PlainParams<N> p;
     const int rows = (int)x.rows, cols = (int)x.cols;
     static_assert(sizeof(p.A2) == sizeof(double) * 2 * N * N, "A2 layout");
     plain_normalise(x.a, rows, cols, x.stride, N, reinterpret_cast<double*>(&p.A2[0][0]), p.phase);
     p.rows = rows;
     p.L = x.L;
+    p.K = x.K;
     p.chunk_begin = x.chunk_begin;
     p.chunk_end = x.chunk_end;
     const unsigned long long per_iter = (unsigned long long)x.grid * kPlainThreads;
@@ -28,21 +50,18 @@ static cudaError_t launch_plain_n(const PlainLaunchArgs& x) {
     p.counter = x.counter;
     p.out = x.out;
     p.fast_row = 0;
-    if constexpr (default_unroll(N) == 2)
-        glynn_plain_rolled_kernel<N><<<x.grid, kPlainThreads, 0, x.stream>>>(p);
-    else
-        glynn_plain_kernel<N><<<x.grid, kPlainThreads, 0, x.stream>>>(p);
+    plain_kernel_fn<N>()<<<x.grid, kPlainThreads, plain_anchor_bytes<N>(), x.stream>>>(p);
     return cudaGetLastError();
 }
 
 template <int N>
 static int occupancy_plain_n(void) {
     int nb = 0;
-    cudaError_t e;
-    if constexpr (default_unroll(N) == 2)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, glynn_plain_rolled_kernel<N>, kPlainThreads, 0);
-    else
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, glynn_plain_kernel<N>, kPlainThreads, 0);
+    cudaError_t e = cudaFuncSetAttribute(plain_kernel_fn<N>(), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)plain_anchor_bytes<N>());
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, plain_kernel_fn<N>(), kPlainThreads,
+                                                          plain_anchor_bytes<N>());
     return e == cudaSuccess ? nb : -1;
 }
 

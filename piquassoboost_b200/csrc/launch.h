@@ -11,7 +11,7 @@ namespace pqb200 {
 struct PlainLaunchArgs {
     const double* a;  // host, interleaved complex, rows x cols, `stride` complex elements per row
     size_t rows, cols, stride;
-    int L;
+    int L, K;  // log2 chunk / sub-chunk length
     unsigned long long chunk_begin, chunk_end;
     int grid;
     double* partials;

@@ -56,7 +56,8 @@ cudaError_t launch_plain_dd(const double* d_a, int n, int L, unsigned long long 
 namespace {
 
 constexpr int kMaxPlainN = 45;
-constexpr int kMaxChunkLog = 12;  // re-seed the running column sums at least every 2^12 updates
+constexpr int kMaxChunkLog = 12;  // full re-seed of the running column sums every 2^12 steps
+constexpr int kSubChunkLog = 8;   // ... and re-derivation from the per-thread anchor every 2^8 steps
 constexpr int kMaxGridBlocks = 4096;
 constexpr int kMaxRepN = 44;
 constexpr unsigned int kMaxRepLen = 4096;  // steps per chunk of the repeated kernel (table size)
@@ -214,6 +215,7 @@ int ensure_devices(int ndev, int* used) {
 struct PlainPlan {
     int N;   // kernel template parameter (columns incl. padding)
     int L;   // log2 chunk length
+    int K;   // log2 sub-chunk length (anchor re-seed period)
     unsigned long long nchunks;
 };
 
@@ -245,6 +247,11 @@ PlainPlan plan_plain(int rows, int cols, int max_resident_threads, unsigned long
         if (L >= lmin && L <= rows - 1) pl.L = L;
     }
     pl.nchunks = 1ull << (rows - 1 - pl.L);
+    pl.K = std::min(pl.L, kSubChunkLog);
+    if (const char* f = getenv("PQB200_FORCE_K")) {  // tuning / debugging aid
+        const int K = atoi(f);
+        if (K >= std::min(2, pl.L) && K <= pl.L) pl.K = K;
+    }
     return pl;
 }
 
@@ -273,6 +280,7 @@ int launch_plain_range(DeviceCtx& c, const double* a, size_t rows, size_t cols, 
     x.cols = cols;
     x.stride = stride;
     x.L = pl.L;
+    x.K = pl.K;
     x.chunk_begin = cb;
     x.chunk_end = ce;
     const unsigned long long want = (ce - cb + kPlainThreads - 1) / kPlainThreads;

@@ -4,6 +4,8 @@ Oracle: the reference's own BBFGPermanentCalculator in long double (oracle/_ref)
 SURVEY.md section 8(c).  Tolerance: 1e-10 relative (BASELINE.json north_star); the tests assert a
 tighter 1e-11 so that regressions in the compensated accumulation are caught early.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -132,3 +134,59 @@ def test_every_chunk_length_gives_the_same_value(pqb, ref, L):
     finally:
         del os.environ["PQB200_FORCE_L"]
     assert relerr(got, want) < TOL, (L, got, want)
+
+
+@pytest.mark.parametrize("N", list(range(3, 46)))
+def test_every_kernel_instantiation(pqb, ref, N):
+    """The kernel is instantiated per column count N with a per-N tuned loop form (static unroll /
+    rolled, chain count): run each one, with and without the anchor re-seeding path (forced chunk
+    length 2^12 > sub-chunk length 2^8), against the reference on a matrix with few rows."""
+    import os
+    rng = np.random.default_rng(1000 + N)
+    if N <= 14:
+        A = haar_unitary(N, N)
+    else:  # 14 x (N-1): rows < cols runs in the N = cols+1 kernel (constant padding column)
+        A = (rng.normal(size=(14, N - 1)) + 1j * rng.normal(size=(14, N - 1))) / np.sqrt(N - 1)
+    want = ref.bbfg(np.ascontiguousarray(A), True)
+    assert relerr(pqb.GlynnPermanent(A).calculate(), want) < TOL, N
+    if A.shape[0] >= 14:
+        os.environ["PQB200_FORCE_L"] = "12"
+        try:
+            got = pqb.GlynnPermanent(A).calculate()
+        finally:
+            del os.environ["PQB200_FORCE_L"]
+        assert relerr(got, want) < TOL, N
+
+
+def _golden_dd():
+    import json
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "plain_dd_reference.json")
+    return json.load(open(path))["cases"]
+
+
+def test_double_double_evaluation_matches_reference_long_double(pqb, ref):
+    """pqb200_permanent_dd (every operation in double-double) against the unmodified reference's long
+    double calculator, live for n=18 and through the committed values the reference produced on CPU
+    for n=32..36 (tests/golden/plain_dd_reference.json, tools/ref_big.py)."""
+    from piquassoboost_b200.Boson_Sampling_Utilities import permanent_double_double
+    A = haar_unitary(18, 18)
+    v, parts = permanent_double_double(A)
+    assert relerr(v, ref.bbfg(A, True)) < 1e-15
+    gold = _golden_dd()
+    A = haar_unitary(32, 32)
+    v, parts = permanent_double_double(A)
+    assert relerr(v, complex(*gold["32"]["ref_long_double"])) < 5e-15  # the long double's own error
+    assert [float(x).hex() for x in parts] == gold["32"]["dd_parts_hex"]  # deterministic, bit for bit
+
+
+@pytest.mark.parametrize("n,tol", [(30, 1e-11), (34, 1e-11), (36, 1e-11), (38, 5e-11), (40, 5e-11)])
+def test_large_haar_unitary_vs_committed_double_double(pqb, n, tol):
+    """BASELINE sizes beyond the CPU reference's reach (n=40: ~2 h on 16 cores): the fast kernel against
+    the committed double-double evaluation, itself pinned to the reference's long double up to n=36.
+    north_star tolerance: 1e-10."""
+    gold = _golden_dd()[str(n)]
+    want = complex(*[float.fromhex(x) for x in gold["dd_parts_hex"]][0::2])
+    got = pqb.GlynnPermanent(haar_unitary(n, n)).calculate()
+    assert relerr(got, want) < tol, (n, got, want)
+    if "ref_long_double" in gold:
+        assert relerr(got, complex(*gold["ref_long_double"])) < tol

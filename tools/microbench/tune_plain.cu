@@ -12,6 +12,9 @@
 #include "../../piquassoboost_b200/csrc/glynn_plain.cuh"
 #include "../../piquassoboost_b200/csrc/plain_host.h"
 using namespace pqb200;
+#ifndef KSUB
+#define KSUB 6
+#endif
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1);} } while (0)
 
 template <int N, int CH, int U>
@@ -23,16 +26,17 @@ template <int N, int CH, int U>
 void run_variant(const std::vector<double>& A, int L, unsigned long long nchunks, double* partials, unsigned int* counter, double* out) {
     static PlainParams<N> p;
     plain_normalise(A.data(), N, N, N, N, reinterpret_cast<double*>(&p.A2[0][0]), p.phase);
-    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, Kern<N, CH, U>::fn, 256, 0));
+    CK(cudaFuncSetAttribute(Kern<N, CH, U>::fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plain_anchor_bytes<N>()));
+    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, Kern<N, CH, U>::fn, 256, plain_anchor_bytes<N>()));
     int grid = 148 * occ;
-    p.fast_row = 0; p.rows = N; p.L = L; p.chunk_begin = 0; p.chunk_end = nchunks;
+    p.fast_row = 0; p.rows = N; p.L = L; p.K = KSUB < L ? KSUB : L; p.chunk_begin = 0; p.chunk_end = nchunks;
     p.iters = (unsigned)((nchunks + (unsigned long long)grid * 256 - 1) / ((unsigned long long)grid * 256));
     p.partials = partials; p.counter = counter; p.out = out;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e30f;
     for (int rep = 0; rep < 3; rep++) {
         cudaEventRecord(e0);
-        Kern<N, CH, U>::fn<<<grid, 256>>>(p);
+        Kern<N, CH, U>::fn<<<grid, 256, plain_anchor_bytes<N>()>>>(p);
         cudaEventRecord(e1); CK(cudaDeviceSynchronize());
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (rep) best = std::min(best, ms);
@@ -56,19 +60,16 @@ void sweep() {
     double* partials; unsigned int* counter; double* out;
     CK(cudaMalloc(&partials, 4 * 8 * 4096)); CK(cudaMalloc(&counter, 4)); CK(cudaMemset(counter, 0, 4)); CK(cudaMalloc(&out, 32));
     run_variant<N, 2, 2>(A, L, nchunks, partials, counter, out);
+    run_variant<N, 3, 2>(A, L, nchunks, partials, counter, out);
     run_variant<N, 4, 2>(A, L, nchunks, partials, counter, out);
+    run_variant<N, 6, 2>(A, L, nchunks, partials, counter, out);
     run_variant<N, 8, 2>(A, L, nchunks, partials, counter, out);
-#ifndef ROLLED_ONLY
     run_variant<N, 2, 4>(A, L, nchunks, partials, counter, out);
     run_variant<N, 4, 4>(A, L, nchunks, partials, counter, out);
     run_variant<N, 8, 4>(A, L, nchunks, partials, counter, out);
     run_variant<N, 2, 8>(A, L, nchunks, partials, counter, out);
     run_variant<N, 4, 8>(A, L, nchunks, partials, counter, out);
     run_variant<N, 8, 8>(A, L, nchunks, partials, counter, out);
-#else
-    run_variant<N, 3, 2>(A, L, nchunks, partials, counter, out);
-    run_variant<N, 6, 2>(A, L, nchunks, partials, counter, out);
-#endif
     cudaFree(partials); cudaFree(counter); cudaFree(out);
 }
 
