@@ -79,6 +79,10 @@ def main():
     inp = np.zeros(40, dtype=np.int64)
     inp[modes] = 1
     shots = 1000 if "--quick" not in sys.argv else 100
+    # first call: context/buffer set-up of the sampler (reported separately); second call: steady state
+    t0 = time.perf_counter()
+    pqb.GeneralizedCliffordsBSimulationStrategy(U, seed=123).simulate(inp, shots)
+    t_first = time.perf_counter() - t0
     t0 = time.perf_counter()
     got = np.array(pqb.GeneralizedCliffordsBSimulationStrategy(U, seed=123).simulate(inp, shots))
     t = time.perf_counter() - t0
@@ -90,7 +94,7 @@ def main():
         want = refbind.simulate_B(U, 123, inp, nref)
         tr = (time.perf_counter() - t0) / nref
         same = bool((got[:nref] == want).all())
-    emit(config="C5", shots=shots, gpu_wall_s=t, gpu_kernel_ms_sum=st["kernel_ms"], launches=st["launches"],
+    emit(config="C5", shots=shots, gpu_wall_s=t, gpu_first_call_wall_s=t_first, gpu_kernel_ms_sum=st["kernel_ms"], launches=st["launches"],
          gpu_s_per_shot=t / shots, ref_s_per_shot=tr, first_20_shots_identical=same,
          mean_occupied_modes=float((got > 0).sum(axis=1).mean()))
     if "--with-c3" in sys.argv:
