@@ -21,8 +21,15 @@
 //      The host tabulates both directions per step; the thread selects with P;
 //   3. C(r,k) = C(r,r-k), so the binomial weight of the low digits is the same for mirrored and
 //      unmirrored threads: it is tabulated per step, pre-multiplied with the alternating parity.
-// Per step: one 16-byte uniform table load, 2N DFMA (update), 4(N-1) DMUL/DFMA (product), 2 DFMA
-// (weighted accumulate).  Accumulation is double-double as in the plain kernel.
+// The step table (signed weight, toggled row, directions) lives in the kernel-parameter constant bank
+// next to the matrix, so that the row index is a uniform value and the row itself comes in through
+// LDCU as a uniform-register operand (a table in global memory pulls the index -- and with it every
+// matrix element -- through the vector path: measured 55 % FP64 pipe utilisation).  The chunk length
+// is therefore bounded by what is left of the 32 KB parameter space: rep_len_max(N) steps.
+// As in glynn_plain.cuh the host normalises the matrix with unit-modulus factors so that the row
+// of the fastest digit (row 1) and the last column are real, and every term is fused with the toggle
+// into the next one.  Per step: (N or 2N-1) DFMA update + 4(N-2) DMUL/DFMA product + 3 (weighted
+// accumulate).  Accumulation is double-double as in the plain kernel.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -36,37 +43,28 @@ namespace pqb200 {
 constexpr int kRepMaxN = 44;      // 16*N*N + header must fit the kernel parameter space
 constexpr int kRepMaxDigits = 44;
 
-// one entry per local step t of a chunk (entry 0: only `w` is used)
+// steps per chunk that fit the parameter space next to the N x N matrix (10 bytes per step)
+__host__ __device__ constexpr int rep_len_max(int n) {
+    return (32764 - 16 * n * n - 704) / 10 > 4096 ? 4096 : (32764 - 16 * n * n - 704) / 10;
+}
+
+// step-table entry and plain product used by the shared-memory kernels (glynn_batch.cuh,
+// laplace_sampler.cuh), which build their tables per CTA
 struct __align__(16) RepStep {
     double w;            // (-1)^t * prod_{low digits} C(r_d, k_d(t))
     int row;             // matrix row toggled going into step t (1..D)
     unsigned int flags;  // bit P: 1 if k increases (column sums -= 2a) for a thread with high parity P
 };
 
-template <int N>
-struct RepParams {
-    double2 A2[N][N];  // 2*a, row 0 = anchor, rows 1..D = digit rows, columns physically repeated
-    int D;             // number of digits (rows - 1)
-    int q;             // number of low digits
-    unsigned int len;  // steps per chunk = prod_{d<q} radix[d]
-    unsigned long long chunk_begin, chunk_end;
-    unsigned int iters;
-    unsigned char radix[kRepMaxDigits];      // r_d + 1
-    unsigned long long weight[kRepMaxDigits];  // prod_{q<=l<d} radix[l]  (d >= q)
-    const RepStep* table;   // [len]
-    const double2* base;    // [2][N]: a_0 + sum_{low d} (+-r_d) a_d for P = 0 / 1   (NOT doubled)
-    const double* binom;    // [D][kRepMaxN+1]: C(r_d, k)
-    const int* low_parity;  // [2]: parity of sum of the low digits' initial k for P = 0 / 1
-    double* partials;
-    unsigned int* counter;
-    double* out;
-};
+__host__ __device__ constexpr int batch_chains(int n) {
+    return n >= 36 ? 2 : n >= 26 ? 4 : n >= 18 ? 8 : n >= 8 ? 4 : n >= 4 ? 2 : 1;
+}
 
 // prod_j c[j]
 template <int N>
 __device__ __forceinline__ void term_prod(const double (&cr)[N], const double (&ci)[N], double& pr,
                                           double& pi) {
-    constexpr int CH = default_chains(N) <= N ? default_chains(N) : 1;
+    constexpr int CH = batch_chains(N) <= N ? batch_chains(N) : 1;
     double qr[CH], qi[CH];
 #pragma unroll
     for (int k = 0; k < CH; k++) {
@@ -85,18 +83,78 @@ __device__ __forceinline__ void term_prod(const double (&cr)[N], const double (&
 }
 
 template <int N>
+struct RepParams {
+    double2 A2[N][N];  // 2*a, row 0 = anchor, rows 1..D = digit rows, columns physically repeated
+    // per local step t of a chunk:  w[t] = (-1)^t * prod_{low digits} C(r_d, k_d(t));
+    // rf[t] = row toggled going INTO step t (1..D) | flags << 8, flag bit P: k increases (column
+    // sums -= 2a) for a thread with high parity P.  rf[len] is a harmless dummy (row 1).
+    double w[rep_len_max(N) + 1];
+    unsigned short rf[rep_len_max(N) + 2];
+    int D;             // number of digits (rows - 1)
+    int q;             // number of low digits
+    unsigned int len;  // steps per chunk = prod_{d<q} radix[d]
+    unsigned long long chunk_begin, chunk_end;
+    unsigned int iters;
+    unsigned char radix[kRepMaxDigits];      // r_d + 1
+    unsigned long long weight[kRepMaxDigits];  // prod_{q<=l<d} radix[l]  (d >= q)
+    const double2* base;    // [2][N]: a_0 + sum_{low d} (+-r_d) a_d for P = 0 / 1   (NOT doubled)
+    const double* binom;    // [D][kRepMaxN+1]: C(r_d, k)
+    int low_parity[2];      // parity of sum of the low digits' initial k for P = 0 / 1
+    double* partials;
+    unsigned int* counter;
+    double* out;
+    double phase[4];        // unit-modulus correction factor (dd complex) applied to the sum
+};
+
+// One weighted term, acc += w * prod_j c[j], fused with the toggle of row `row` into the next term
+// (see term_toggle in glynn_plain.cuh).  REALROW: the toggled row is real (row 1).
+template <int N, int CH, bool REALROW>
+__device__ __forceinline__ void rep_term_toggle(const RepParams<N>& p, int row, double sg, double w,
+                                                double (&cr)[N], double (&ci)[N], double& acc_re,
+                                                double& acc_im) {
+    constexpr int M = N - 1;  // complex factors; column N-1 is real
+    constexpr int C = CH < M ? CH : M;
+    double qr[C], qi[C];
+#pragma unroll
+    for (int k = 0; k < C; k++) {
+        qr[k] = cr[k];
+        qi[k] = ci[k];
+        cr[k] = fma(sg, p.A2[row][k].x, cr[k]);
+        if (!REALROW) ci[k] = fma(sg, p.A2[row][k].y, ci[k]);
+    }
+#pragma unroll
+    for (int j = C; j < M; j++) {
+        cmul(qr[j % C], qi[j % C], cr[j], ci[j]);
+        cr[j] = fma(sg, p.A2[row][j].x, cr[j]);
+        if (!REALROW) ci[j] = fma(sg, p.A2[row][j].y, ci[j]);
+    }
+#pragma unroll
+    for (int v = 1; v < C; v *= 2) {
+#pragma unroll
+        for (int k = 0; k + v < C; k += 2 * v) cmul(qr[k], qi[k], qr[k + v], qi[k + v]);
+    }
+    const double f = w * cr[N - 1];
+    cr[N - 1] = fma(sg, p.A2[row][N - 1].x, cr[N - 1]);
+    acc_re = fma(qr[0], f, acc_re);
+    acc_im = fma(qi[0], f, acc_im);
+}
+
+__host__ __device__ constexpr int rep_chains(int n) { return n >= 26 ? 4 : n >= 8 ? 4 : n >= 4 ? 2 : 1; }
+
+template <int N>
 __device__ __forceinline__ void rep_toggle(const RepParams<N>& p, int row, double sg,
                                            double (&cr)[N], double (&ci)[N]) {
 #pragma unroll
     for (int j = 0; j < N; j++) {
         cr[j] = fma(sg, p.A2[row][j].x, cr[j]);
-        ci[j] = fma(sg, p.A2[row][j].y, ci[j]);
+        if (j < N - 1) ci[j] = fma(sg, p.A2[row][j].y, ci[j]);
     }
 }
 
 template <int N>
 __global__ void __launch_bounds__(kPlainThreads, 1)
 glynn_repeated_kernel(const __grid_constant__ RepParams<N> p) {
+    constexpr int CH = rep_chains(N);
     const int D = p.D, q = p.q;
     const unsigned int len = p.len;
     const unsigned long long nthreads = (unsigned long long)gridDim.x * kPlainThreads;
@@ -127,7 +185,7 @@ glynn_repeated_kernel(const __grid_constant__ RepParams<N> p) {
         for (int j = 0; j < N; j++) {
             const double2 b = p.base[P * N + j];
             cr[j] = b.x;
-            ci[j] = b.y;
+            if (j < N - 1) ci[j] = b.y;
         }
         // pass 2: add the high rows, (r - 2k) * a = 0.5 (r - 2k) * (2a)
         par = 0;
@@ -139,25 +197,19 @@ glynn_repeated_kernel(const __grid_constant__ RepParams<N> p) {
             par ^= k & 1;
             rep_toggle<N>(p, d + 1, 0.5 * (double)(radix - 1 - 2 * k), cr, ci);
         }
-        // ---- sweep the low digits
+        // ---- sweep the low digits: term t, then the toggle into term t+1 (table index t+1)
         cdd cacc = cdd_zero();
         double bs_re = 0.0, bs_im = 0.0;
-        {
-            double pr, pi;
-            term_prod<N>(cr, ci, pr, pi);
-            const double w = p.table[0].w;
-            bs_re = w * pr;
-            bs_im = w * pi;
-        }
 #pragma unroll 1
-        for (unsigned int t = 1; t < len; t++) {
-            const RepStep e = p.table[t];
-            const double sg = ((e.flags >> P) & 1u) ? -1.0 : 1.0;
-            rep_toggle<N>(p, e.row, sg, cr, ci);
-            double pr, pi;
-            term_prod<N>(cr, ci, pr, pi);
-            bs_re = fma(e.w, pr, bs_re);
-            bs_im = fma(e.w, pi, bs_im);
+        for (unsigned int t = 0; t < len; t++) {
+            const double w = p.w[t];
+            const unsigned int rf = p.rf[t + 1];
+            const int row = (int)(rf & 0xffu);
+            const double sg = ((rf >> (8 + P)) & 1u) ? -1.0 : 1.0;
+            if (row == 1)
+                rep_term_toggle<N, CH, true>(p, row, sg, w, cr, ci, bs_re, bs_im);
+            else
+                rep_term_toggle<N, CH, false>(p, row, sg, w, cr, ci, bs_re, bs_im);
             if ((t & 7u) == 7u) {  // fold into the double-double accumulator every 8 terms
                 dd_add_d(cacc.re, bs_re);
                 dd_add_d(cacc.im, bs_im);
@@ -174,7 +226,7 @@ glynn_repeated_kernel(const __grid_constant__ RepParams<N> p) {
         scaled.im = dd_mul_d(cacc.im, f);
         cdd_add(tot, scaled);
     }
-    grid_reduce_cdd<kPlainThreads>(tot, p.partials, p.counter, p.out);
+    grid_reduce_cdd<kPlainThreads>(tot, p.partials, p.counter, p.out, p.phase);
 }
 
 }  // namespace pqb200

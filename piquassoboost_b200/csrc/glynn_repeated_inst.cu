@@ -2,6 +2,7 @@
 // registers the launchers (same scheme as glynn_plain_inst.cu).
 #include "glynn_repeated.cuh"
 #include "launch.h"
+#include "repeated_host.h"
 
 #ifndef PQB_NLO
 #error "define PQB_NLO and PQB_NHI"
@@ -36,10 +37,20 @@ static cudaError_t launch_rep_n(const RepLaunchArgs& x) {
         p.weight[d] = d < p.D ? x.weight[d] : 1;
         if (p.weight[d] == 0) p.weight[d] = 1;
     }
-    p.table = (const RepStep*)x.table;
+    if (x.len > (unsigned int)rep_len_max(N)) return cudaErrorInvalidValue;
+    const RepStepHost* tab = (const RepStepHost*)x.table;
+    for (unsigned int t = 0; t < x.len; t++) {
+        p.w[t] = tab[t].w;
+        p.rf[t] = (unsigned short)((unsigned int)tab[t].row | (tab[t].flags << 8));
+    }
+    p.rf[0] = 1;
+    p.w[x.len] = 0.0;
+    p.rf[x.len] = 1;  // dummy toggle behind the last term of a chunk (row 1, never used)
     p.base = (const double2*)x.base;
     p.binom = x.binom;
-    p.low_parity = x.low_parity;
+    p.low_parity[0] = x.low_parity[0];
+    p.low_parity[1] = x.low_parity[1];
+    for (int k = 0; k < 4; k++) p.phase[k] = x.phase[k];
     p.partials = x.partials;
     p.counter = x.counter;
     p.out = x.out;

@@ -32,10 +32,11 @@ struct RepLaunchArgs {
     int grid;
     const unsigned char* radix;        // [R-1]
     const unsigned long long* weight;  // [R-1]
-    const void* table;                 // device, RepStep[len]
+    const void* table;                 // HOST, RepStepHost[len] (copied into the kernel parameters)
     const void* base;                  // device, double2[2][N]
     const double* binom;               // device, [R-1][kRepBinomStride]
-    const int* low_parity;             // device, [2]
+    int low_parity[2];
+    double phase[4];                   // dd complex correction factor of the normalisation
     double* partials;
     unsigned int* counter;
     double* out;

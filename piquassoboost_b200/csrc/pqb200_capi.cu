@@ -55,12 +55,17 @@ cudaError_t launch_plain_dd(const double* d_a, int n, int L, unsigned long long 
 
 namespace {
 
+// keep in sync with rep_len_max() in glynn_repeated.cuh (steps per chunk that fit the parameter space)
+inline int rep_len_max_host(int n) {
+    const int v = (32764 - 16 * n * n - 704) / 10;
+    return v > 4096 ? 4096 : v;
+}
+
 constexpr int kMaxPlainN = 45;
 constexpr int kMaxChunkLog = 12;  // full re-seed of the running column sums every 2^12 steps
 constexpr int kSubChunkLog = 8;   // ... and re-derivation from the per-thread anchor every 2^8 steps
 constexpr int kMaxGridBlocks = 4096;
 constexpr int kMaxRepN = 44;
-constexpr unsigned int kMaxRepLen = 4096;  // steps per chunk of the repeated kernel (table size)
 
 struct DeviceCtx {
     int dev = -1;
@@ -73,10 +78,8 @@ struct DeviceCtx {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int occ[kPlainTableSize];
     // repeated-row kernel tables (device): step table, base vectors, binomials, low parities
-    void* rep_table = nullptr;
     void* rep_base = nullptr;
     double* rep_binom = nullptr;
-    int* rep_lowpar = nullptr;
     // batch path: growable device buffers (matrix data, job descriptors, results, pmf scratch)
     void* b_u = nullptr;      size_t b_u_cap = 0;
     void* b_jobs = nullptr;   size_t b_jobs_cap = 0;
@@ -176,10 +179,8 @@ int get_device(int dev, DeviceCtx** out) {
         CUDA_TRY(cudaMallocHost(&c.h_out, sizeof(double) * 4));
         CUDA_TRY(cudaEventCreate(&c.e0));
         CUDA_TRY(cudaEventCreate(&c.e1));
-        CUDA_TRY(cudaMalloc(&c.rep_table, 16 * (size_t)kMaxRepLen));
         CUDA_TRY(cudaMalloc(&c.rep_base, 16 * 2 * (size_t)kMaxRepN));
         CUDA_TRY(cudaMalloc(&c.rep_binom, sizeof(double) * kMaxRepN * kRepBinomStride));
-        CUDA_TRY(cudaMalloc(&c.rep_lowpar, 2 * sizeof(int)));
         for (int i = 0; i < kPlainTableSize; i++) c.occ[i] = 0;
         c.dev = dev;
     }
@@ -369,10 +370,8 @@ void pqb200_shutdown(void) {
         cudaFree(c.partials);
         cudaFree(c.counter);
         cudaFree(c.d_out);
-        cudaFree(c.rep_table);
         cudaFree(c.rep_base);
         cudaFree(c.rep_binom);
-        cudaFree(c.rep_lowpar);
         cudaFree(c.b_u);
         cudaFree(c.b_jobs);
         cudaFree(c.b_out);
@@ -534,9 +533,10 @@ static int repeated_locked(const double* a, size_t rows, size_t cols, size_t str
     if (pr.all_single)  // every digit is binary: this is a plain permanent of the expanded matrix
         return plain_multi_device(pr.mat.data(), (size_t)pr.R, (size_t)pr.N, (size_t)pr.N, used,
                                   (size_t)pr.photons, out);
+    rep_normalise(pr);
     RepPlan pl;
-    rep_plan(pr, g_devs[0].sm_count * kPlainThreads, (unsigned long long)used, kMaxRepLen,
-             kRepBinomStride, pl);
+    rep_plan(pr, g_devs[0].sm_count * kPlainThreads, (unsigned long long)used,
+             (unsigned int)rep_len_max_host(pr.N), kRepBinomStride, pl);
     if ((unsigned long long)used > pl.nchunks) used = (int)pl.nchunks;
     std::vector<double> parts(4 * (size_t)used);
     static_assert(sizeof(RepStepHost) == 16, "step table layout");
@@ -545,10 +545,8 @@ static int repeated_locked(const double* a, size_t rows, size_t cols, size_t str
     for (int d = 0; d < used; d++) {
         DeviceCtx& c = g_devs[d];
         CUDA_TRY(cudaSetDevice(c.dev));
-        CUDA_TRY(cudaMemcpyAsync(c.rep_table, pl.table.data(), 16 * (size_t)pl.len, cudaMemcpyHostToDevice, c.stream));
         CUDA_TRY(cudaMemcpyAsync(c.rep_base, pl.base.data(), 16 * 2 * (size_t)pr.N, cudaMemcpyHostToDevice, c.stream));
         CUDA_TRY(cudaMemcpyAsync(c.rep_binom, pl.binom.data(), sizeof(double) * pl.binom.size(), cudaMemcpyHostToDevice, c.stream));
-        CUDA_TRY(cudaMemcpyAsync(c.rep_lowpar, pl.low_parity, 2 * sizeof(int), cudaMemcpyHostToDevice, c.stream));
         RepLaunchArgs x;
         x.mat = pr.mat.data();
         x.R = pr.R;
@@ -561,10 +559,12 @@ static int repeated_locked(const double* a, size_t rows, size_t cols, size_t str
         x.grid = (int)std::min<unsigned long long>(want, (unsigned long long)std::min(kMaxGridBlocks, c.sm_count));
         x.radix = pl.radix;
         x.weight = pl.weight;
-        x.table = c.rep_table;
+        x.table = pl.table.data();
         x.base = c.rep_base;
         x.binom = c.rep_binom;
-        x.low_parity = c.rep_lowpar;
+        x.low_parity[0] = pl.low_parity[0];
+        x.low_parity[1] = pl.low_parity[1];
+        for (int k = 0; k < 4; k++) x.phase[k] = pr.phase[k];
         x.partials = c.partials;
         x.counter = c.counter;
         x.out = c.d_out;

@@ -6,7 +6,10 @@
 #pragma once
 #include <stdint.h>
 
+#include <math.h>
+
 #include <algorithm>
+#include <complex>
 #include <string>
 #include <vector>
 
@@ -23,6 +26,7 @@ struct RepPrepared {
     std::vector<double> mat;  // R x N complex, interleaved, row-major
     std::vector<int> r;       // r[d] = multiplicity of row d+1, d = 0..R-2 (all >= 1)
     int photons = 0;
+    double phase[4] = {1.0, 0.0, 0.0, 0.0};  // dd complex factor the kernel's sum is multiplied with
 };
 
 // Reference semantics: BBFGPermanentCalculatorRepeated.cpp:74-141 and .hpp:74-140.
@@ -114,6 +118,50 @@ inline int rep_prepare(const double* a, size_t rows, size_t cols, size_t stride,
     }
     out.all_single = std::all_of(out.r.begin(), out.r.end(), [](int m) { return m == 1; });
     return 0;
+}
+
+// Unit-modulus row/column factors that make row 1 (the fastest digit's row) and the last column of
+// `mat` real (glynn_repeated.cuh; same idea and numerics as plain_host.h).  The expanded matrix holds
+// row i of `mat` r_i times (the anchor row 0 once), so a row factor enters the permanent with that
+// power; out.phase receives the inverse of the total factor as a double-double complex number.
+inline void rep_normalise(RepPrepared& out) {
+    typedef std::complex<long double> cld;
+    const int R = out.R, N = out.N;
+    std::vector<cld> b((size_t)R * N);
+    for (size_t k = 0; k < b.size(); k++) b[k] = cld(out.mat[2 * k], out.mat[2 * k + 1]);
+    cld corr(1.0L, 0.0L);
+    for (int j = 0; j < N; j++) {
+        const cld v = b[(size_t)1 * N + j];
+        const long double m = hypotl(v.real(), v.imag());
+        if (m == 0.0L || v.imag() == 0.0L) continue;
+        const cld f = std::conj(v) / m;
+        for (int i = 0; i < R; i++) b[(size_t)i * N + j] *= f;
+        b[(size_t)1 * N + j] = cld(m, 0.0L);
+        corr *= std::conj(f) / std::norm(f);
+    }
+    for (int i = 0; i < R; i++) {
+        if (i == 1) continue;
+        const cld v = b[(size_t)i * N + (N - 1)];
+        const long double m = hypotl(v.real(), v.imag());
+        if (m == 0.0L || v.imag() == 0.0L) continue;
+        const cld f = std::conj(v) / m;
+        for (int j = 0; j < N; j++) b[(size_t)i * N + j] *= f;
+        b[(size_t)i * N + (N - 1)] = cld(m, 0.0L);
+        const cld inv = std::conj(f) / std::norm(f);
+        const int mult = i == 0 ? 1 : out.r[i - 1];
+        for (int k = 0; k < mult; k++) corr *= inv;
+    }
+    for (size_t k = 0; k < b.size(); k++) {
+        out.mat[2 * k] = (double)b[k].real();
+        out.mat[2 * k + 1] = (double)b[k].imag();
+    }
+    for (int i = 0; i < R; i++) out.mat[2 * ((size_t)i * N + (N - 1)) + 1] = 0.0;
+    for (int j = 0; j < N; j++) out.mat[2 * ((size_t)1 * N + j) + 1] = 0.0;
+    const double rh = (double)corr.real(), ih = (double)corr.imag();
+    out.phase[0] = rh;
+    out.phase[1] = (double)(corr.real() - (long double)rh);
+    out.phase[2] = ih;
+    out.phase[3] = (double)(corr.imag() - (long double)ih);
 }
 
 struct RepStepHost {

@@ -122,3 +122,25 @@ def test_connector_permanent_hook(pqb, ref):
     res = connector.permanent_function_batch(U, [a, [2, 2, 0, 0, 0, 0]], [b])
     assert relerr(res[0][0], ref.bbfg_repeated(U, a, b, True)) < TOL
     assert relerr(res[1][0], ref.bbfg_repeated(U, [2, 2, 0, 0, 0, 0], b, True)) < TOL
+
+
+@pytest.mark.parametrize("photons", list(range(3, 45)))
+def test_every_repeated_kernel_instantiation(pqb, ref, photons):
+    """glynn_repeated_kernel is instantiated per total photon number N (= physically repeated
+    columns): run each one on 6 modes with high multiplicities (small mixed-radix Gray space, so that
+    the reference's long double answer is cheap).  Many photons in few modes is the ill-conditioned
+    corner of the formula (huge binomial-weighted terms cancelling): there the bound is north_star's
+    1e-10 and "no worse than 10x the reference's own double path", below 25 photons the usual 1e-11."""
+    rng = np.random.default_rng(500 + photons)
+    U = haar_unitary(6, 77)
+    for trial in range(2):
+        inp = rng.multinomial(photons, [1 / 6] * 6).astype(np.int64)
+        out = rng.multinomial(photons, [0.3, 0.2, 0.2, 0.1, 0.1, 0.1] if trial else [1 / 6] * 6).astype(np.int64)
+        want = ref.bbfg_repeated(U, inp, out, True)
+        got = pqb.BBFGRepeatedPermanentCalculatorDouble(U, inp, out).calculate()
+        err = relerr(got, want)
+        if photons <= 24:
+            assert err < TOL, (photons, inp, out, got, want)
+        else:
+            ref_double_err = relerr(ref.bbfg_repeated(U, inp, out, False), want)
+            assert err < 1e-10 or err < 10 * ref_double_err, (photons, inp, out, got, want, ref_double_err)
