@@ -1,0 +1,170 @@
+"""CPU tests of the HOST logic in front of the kernels (no GPU): the unit-modulus normalisation of
+plain_host.h / rep_normalise and the repeated-row planning of repeated_host.h (step table, base vectors,
+binomials, chunk decomposition).  The headers are compiled into a small test library
+(tests/cpp/host_logic.cpp) and the kernels' sweeps are emulated in numpy / Python integers; the oracle
+(C restatement of the reference, long double) is the checker."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import haar_unitary, relerr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int)
+_lp = ctypes.POINTER(ctypes.c_int64)
+
+
+@pytest.fixture(scope="module")
+def hl(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("hl") / "libhostlogic.so")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-I/usr/local/cuda/include", "-o", so,
+                    os.path.join(ROOT, "tests", "cpp", "host_logic.cpp")], check=True, capture_output=True)
+    return ctypes.CDLL(so)
+
+
+def _oracle(A):
+    from oracle import oraclebind
+    return oraclebind.bbfg(np.ascontiguousarray(A), oraclebind.LONG_DOUBLE)
+
+
+def _normalise(hl, A):
+    A = np.ascontiguousarray(A, dtype=np.complex128)
+    rows, cols = A.shape
+    N = hl.hl_plain_cols(rows, cols)
+    a2 = np.zeros((N, N), dtype=np.complex128)
+    phase = np.zeros(4)
+    hl.hl_plain_normalise(A.ctypes.data_as(_dp), rows, cols, ctypes.c_size_t(cols), N, a2.ctypes.data_as(_dp),
+                          phase.ctypes.data_as(_dp))
+    return N, a2, complex(phase[0] + phase[1], phase[2] + phase[3])
+
+
+@pytest.mark.parametrize("shape", [(2, 2), (3, 3), (7, 7), (12, 12), (5, 4), (4, 6), (9, 9)])
+def test_plain_normalisation_keeps_the_permanent(hl, shape):
+    """The kernel's contract (real Gray-bit-0 row, real last column, kernel row order) and the value:
+    the Glynn sum of the normalised matrix times the correction factor is the reference's value."""
+    rng = np.random.default_rng(shape[0] * 31 + shape[1])
+    A = rng.normal(size=shape) + 1j * rng.normal(size=shape)
+    if shape == (9, 9):
+        A[8, 3] = 0.0      # zeros in the row / column that is made real must be harmless
+        A[2, 8] = 0.0
+    rows, cols = shape
+    N, a2, corr = _normalise(hl, A)
+    assert abs(abs(corr) - 1.0) < 1e-15
+    assert np.all(a2[0].imag == 0.0) and np.all(a2[:, N - 1].imag == 0.0)
+    assert np.allclose(np.abs(a2[:rows, :cols]), 2 * np.abs(np.vstack([A[1:][::-1], A[:1]])), rtol=1e-15)
+    # emulate the kernel's sum: row rows-1 has delta = +1, row k is toggled by Gray bit k
+    total = 0.0
+    for g in range(1 << (rows - 1)):
+        gray = g ^ (g >> 1)
+        c = 0.5 * a2[rows - 1].copy()
+        for k in range(rows - 1):
+            c += (-0.5 if (gray >> k) & 1 else 0.5) * a2[k]
+        total += (-1) ** bin(gray).count("1") * np.prod(c)
+    got = total * corr / 2.0 ** (rows - 1)
+    assert relerr(got, _oracle(A)) < 1e-12
+
+
+def _rep_plan(hl, U, inp, out, max_len, normalise=1):
+    U = np.ascontiguousarray(U, dtype=np.complex128)
+    rows, cols = U.shape
+    rm = np.ascontiguousarray(out, dtype=np.int64)
+    cm = np.ascontiguousarray(inp, dtype=np.int64)
+    P = int(rm.sum())
+    mat = np.zeros((P + 1, max(P, 1)), dtype=np.complex128)
+    r = np.zeros(64, dtype=np.int32)
+    tw = np.zeros(max_len + 1)
+    trow = np.zeros(max_len + 1, dtype=np.int32)
+    tfl = np.zeros(max_len + 1, dtype=np.int32)
+    base = np.zeros((2, max(P, 1)), dtype=np.complex128)
+    radix = np.zeros(64, dtype=np.int32)
+    weight = np.zeros(64, dtype=np.uint64)
+    binom = np.zeros(64 * 45)
+    phase = np.zeros(4)
+    misc = np.zeros(8, dtype=np.int64)
+    triv = np.zeros(2)
+    rc = hl.hl_rep_plan(U.ctypes.data_as(_dp), ctypes.c_size_t(rows), ctypes.c_size_t(cols), ctypes.c_size_t(cols),
+                        rm.ctypes.data_as(_lp), cm.ctypes.data_as(_lp), max_len, normalise, triv.ctypes.data_as(_dp),
+                        mat.ctypes.data_as(_dp), r.ctypes.data_as(_ip), tw.ctypes.data_as(_dp), trow.ctypes.data_as(_ip),
+                        tfl.ctypes.data_as(_ip), base.ctypes.data_as(_dp), radix.ctypes.data_as(_ip),
+                        weight.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), binom.ctypes.data_as(_dp),
+                        phase.ctypes.data_as(_dp), misc.ctypes.data_as(_lp))
+    return rc, dict(mat=mat, r=r, tw=tw, trow=trow, tfl=tfl, base=base, radix=radix, weight=weight,
+                    binom=binom.reshape(64, 45), phase=complex(phase[0] + phase[1], phase[2] + phase[3]),
+                    R=int(misc[0]), N=int(misc[1]), q=int(misc[2]), len=int(misc[3]), nchunks=int(misc[4]),
+                    lowpar=(int(misc[5]), int(misc[6])), photons=int(misc[7]), triv=complex(triv[0], triv[1]))
+
+
+def _emulate_repeated_kernel(pl):
+    """glynn_repeated_kernel in Python: one 'thread' per chunk, term t then the toggle of table entry t+1."""
+    R, N, q, length = pl["R"], pl["N"], pl["q"], pl["len"]
+    D = R - 1
+    mat = pl["mat"].reshape(-1)[:R * N].reshape(R, N)
+    A2 = 2.0 * mat
+    total = 0.0
+    for cc in range(pl["nchunks"]):
+        par, ksum, whigh = 0, 0, 1.0
+        ks = {}
+        for d in range(D - 1, q - 1, -1):
+            radix = int(pl["radix"][d])
+            cnt = (cc // int(pl["weight"][d])) % radix
+            k = radix - 1 - cnt if par else cnt
+            par ^= k & 1
+            ksum += k
+            whigh *= pl["binom"][d, k]
+            ks[d] = k
+        P = par
+        c = pl["base"][P, :N].copy()
+        for d in range(D - 1, q - 1, -1):
+            c += 0.5 * (int(pl["radix"][d]) - 1 - 2 * ks[d]) * A2[d + 1]
+        acc = 0.0
+        for t in range(length):
+            acc += pl["tw"][t] * np.prod(c)
+            if t + 1 < length:
+                row, fl = int(pl["trow"][t + 1]), int(pl["tfl"][t + 1])
+                c += (-1.0 if (fl >> P) & 1 else 1.0) * A2[row]
+        f = -whigh if (ksum + pl["lowpar"][P]) & 1 else whigh
+        total += f * acc
+    return total * pl["phase"] / 2.0 ** (pl["photons"] - 1)
+
+
+@pytest.mark.parametrize("case", [
+    ([2, 1, 0, 1], [1, 1, 2, 0], 64),
+    ([3, 0, 2, 0, 1], [1, 2, 1, 1, 1], 12),      # short chunks: several high digits
+    ([0, 4, 0, 3], [2, 2, 2, 1], 5),
+    ([2, 2, 2, 2, 0, 0], [1, 1, 1, 1, 2, 2], 9),
+    ([5, 0, 0, 0], [1, 1, 1, 2], 100),             # a single repeated column after transposition
+])
+@pytest.mark.parametrize("normalise", [0, 1])
+def test_repeated_plan_tables_reproduce_the_reference(hl, case, normalise):
+    from oracle import oraclebind
+    inp, out, max_len = case
+    m = len(inp)
+    U = haar_unitary(m, 40 + m)
+    rc, pl = _rep_plan(hl, U, inp, out, max_len, normalise)
+    assert rc == 0, rc
+    assert pl["len"] <= max_len
+    if normalise:
+        mat = pl["mat"].reshape(-1)[:pl["R"] * pl["N"]].reshape(pl["R"], pl["N"])
+        assert np.all(mat[1].imag == 0.0) and np.all(mat[:, -1].imag == 0.0)
+    want = oraclebind.bbfg_repeated(np.ascontiguousarray(U), np.array(inp), np.array(out), oraclebind.LONG_DOUBLE)
+    assert relerr(_emulate_repeated_kernel(pl), want) < 1e-12
+
+
+def test_repeated_prepare_edge_cases(hl):
+    U = haar_unitary(4, 3)
+    rc, pl = _rep_plan(hl, U, [0, 0, 0, 0], [0, 0, 0, 0], 16)
+    assert rc == 1 and pl["triv"] == 1.0                      # empty permanent is 1
+    rc, _ = _rep_plan(hl, U, [1, 1, 0, 0], [1, 0, 0, 0], 16)
+    assert rc == -3                                           # photon-number mismatch
+    rc, pl = _rep_plan(hl, U, [1, 1, 1, 0], [0, 1, 1, 1], 16)
+    assert rc == 2                                            # all singles: plain route
+    rc, pl = _rep_plan(hl, U, [0, 0, 1, 0], [1, 0, 0, 0], 16)
+    assert rc == 1                                            # single row: product of entries
+    assert relerr(pl["triv"], U[0, 2]) < 1e-15
+    rc, pl = _rep_plan(hl, U, [0, 2, 0, 1], [3, 0, 0, 0], 16)  # one row three times: 3! * prod
+    assert rc == 0
+    assert relerr(_emulate_repeated_kernel(pl), 6 * U[0, 1] ** 2 * U[0, 3]) < 1e-13
