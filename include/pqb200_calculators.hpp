@@ -24,7 +24,14 @@
 
 namespace pqb200 {
 
+// Inside the reference tree define PQB200_COMPLEX16 to pic::Complex16 before including this header
+// (common/source/PicComplex.hpp:34-409: layout-compatible with std::complex<double>, constructible
+// from (re, im)); stand-alone users get std::complex<double>.
+#ifdef PQB200_COMPLEX16
+using Complex16 = PQB200_COMPLEX16;
+#else
 using Complex16 = std::complex<double>;
+#endif
 
 inline void check(int rc) {
     if (rc != PQB200_OK) throw std::string(pqb200_last_error());

@@ -33,3 +33,26 @@ def test_shim_known_answer_on_gpu(tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "repeated=(-1," in res.stdout
+
+
+REF_TYPES_EXE = os.path.join(ROOT, "oracle", "_ref", "shim_reference_types")
+
+
+def test_shim_compiles_against_the_reference_container_types():
+    """In the dev container (reference tree present) `make -C oracle ref` instantiates the shim with
+    pic::matrix / pic::PicState_int64 from the reference's own headers; without a GPU it must throw the
+    reference's error type (std::string -> exit code 10)."""
+    if not os.path.isdir("/root/reference/piquassoboost"):
+        pytest.skip("reference tree not present")
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True, capture_output=True)
+    res = subprocess.run([REF_TYPES_EXE], capture_output=True, text=True)
+    assert res.returncode in (0, 10), res.stdout + res.stderr
+
+
+@pytest.mark.gpu
+def test_shim_with_reference_types_known_answer_on_gpu():
+    if not os.path.exists(REF_TYPES_EXE):
+        pytest.skip("oracle/_ref/shim_reference_types was not built (needs the reference tree)")
+    res = subprocess.run([REF_TYPES_EXE], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "repeated=(-1," in res.stdout
