@@ -179,7 +179,7 @@ __host__ __device__ constexpr int default_unroll(int n) {
 __host__ __device__ constexpr int default_chains(int n) {
     return n >= 45 ? 2 : n == 44 ? 4 : n == 43 ? 4 : n == 42 ? 2 : n == 41 ? 4 : n == 40 ? 4 : n == 39 ? 2
          : n == 38 ? 4 : n == 37 ? 8 : n == 36 ? 8 : n == 35 ? 4 : n == 34 ? 6 : n == 33 ? 6 : n == 32 ? 4
-         : n == 31 ? 6 : n == 30 ? 8 : n == 29 ? 6 : n == 28 ? 8 : n == 27 ? 8 : n == 26 ? 2 : n == 25 ? 2
+         : n == 31 ? 7 : n == 30 ? 8 : n == 29 ? 7 : n == 28 ? 7 : n == 27 ? 8 : n == 26 ? 2 : n == 25 ? 2
          : n == 24 ? 8 : n == 23 ? 4 : n >= 17 ? 2 : n >= 8 ? 4 : n >= 4 ? 2 : 1;
 }
 

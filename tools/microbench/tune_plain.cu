@@ -70,6 +70,10 @@ void sweep() {
     run_variant<N, 2, 8>(A, L, nchunks, partials, counter, out);
     run_variant<N, 4, 8>(A, L, nchunks, partials, counter, out);
     run_variant<N, 8, 8>(A, L, nchunks, partials, counter, out);
+    run_variant<N, 5, 2>(A, L, nchunks, partials, counter, out);
+    run_variant<N, 7, 2>(A, L, nchunks, partials, counter, out);
+    run_variant<N, 6, 8>(A, L, nchunks, partials, counter, out);
+    run_variant<N, 3, 8>(A, L, nchunks, partials, counter, out);
     cudaFree(partials); cudaFree(counter); cudaFree(out);
 }
 
