@@ -66,6 +66,24 @@ int pqb200_permanent_shard(const double* a, size_t rows, size_t cols, size_t str
  * exact 2^-(rows-1) scaling (reference: BBFGPermanentCalculator.hpp:227-232). */
 int pqb200_permanent_combine(const double* partials_dd, size_t count, size_t rows, double out[2]);
 
+/* ---- one process per GPU, collective inside the library (NCCL resolved with dlopen at first use) ----
+ * the Gray-code space of ONE permanent is sharded over the ranks and ONE
+ * ncclAllGather of 4 doubles per rank, enqueued on the compute stream directly behind the kernel,
+ * combines the partials; every rank folds them in rank order (double-double) and gets the same bits.
+ * The reference has no counterpart (its MPI mode shards shots:
+ * sampling/simulation_strategies/source/CGeneralizedCliffordsBSimulationStrategy.cpp:158-231).
+ *   rank 0: pqb200_nccl_unique_id(id); broadcast the 128 bytes with the job's launcher (MPI, torch, file);
+ *   every rank: pqb200_nccl_init(local_device, rank, world, id); then pqb200_permanent_nccl(...) collectively. */
+int pqb200_nccl_unique_id(char id[128]);
+int pqb200_nccl_init(int device, int rank, int world, const char id[128]);
+int pqb200_nccl_shutdown(void);
+int pqb200_permanent_nccl(const double* a, size_t rows, size_t cols, size_t stride, double out[2]);
+/* Non-blocking form: kernel + all-gather enqueued on `stream` (a cudaStream_t; NULL = the library's own);
+ * d_gathered (device, 4*world doubles; NULL = the library's buffer) receives the partials in rank order,
+ * to be folded with pqb200_permanent_combine after the caller synchronised the stream. */
+int pqb200_permanent_nccl_async(const double* a, size_t rows, size_t cols, size_t stride,
+                                double* d_gathered, void* stream);
+
 /* perm(A) of a square matrix (2 <= n <= 45) with EVERY operation in double-double arithmetic
  * (~106 mantissa bits): the engine's counterpart of the reference's extended-precision request
  *   BBFGPermanentCalculator::calculate(mtx, use_extended=true)  sampling/source/BBFGPermanentCalculator.cpp:109-116

@@ -46,6 +46,14 @@ _SIGNATURES = {
         ctypes.c_int,
         [c_double_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, c_double_p],
     ),
+    "pqb200_nccl_unique_id": (ctypes.c_int, [ctypes.c_char_p]),
+    "pqb200_nccl_init": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]),
+    "pqb200_nccl_shutdown": (ctypes.c_int, []),
+    "pqb200_permanent_nccl": (
+        ctypes.c_int, [c_double_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, c_double_p]),
+    "pqb200_permanent_nccl_async": (
+        ctypes.c_int,
+        [c_double_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
     "pqb200_permanent_shard": (
         ctypes.c_int,
         [c_double_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,

@@ -352,6 +352,7 @@ void combine_partials(const double* parts, size_t count, size_t rows, double out
 extern "C" {
 
 static void lap_release_all();
+static void nccl_release_locked();
 
 const char* pqb200_last_error(void) { return g_err.c_str(); }
 const char* pqb200_version(void) { return "pqb200 0.1 (sm_100a)"; }
@@ -382,6 +383,7 @@ void pqb200_shutdown(void) {
         cudaEventDestroy(c.e1);
         cudaStreamDestroy(c.stream);
     }
+    nccl_release_locked();
     lap_release_all();
     g_devs.clear();
     g_visible = -1;
@@ -645,6 +647,7 @@ static int grow(void** p, size_t* cap, size_t need) {
     return PQB200_OK;
 }
 
+#include "nccl_capi.inc"
 #include "sampler_capi.inc"
 
 struct BatchItem {

@@ -1,7 +1,9 @@
 """One-process-per-GPU evaluation of a single permanent: every rank computes its shard of the Gray
-index space (pqb200_permanent_shard), the 4-double partials are all-gathered with
-torch.distributed (NCCL on GPUs; gloo in the CPU tests) and folded in rank order with
-double-double adds (pqb200_permanent_combine).  torch is plumbing only: the compute is the C ABI.
+index space, the 4-double partials are all-gathered and folded in rank order with double-double adds.
+Two routes: `nccl_init` + `permanent_nccl` keep the collective INSIDE the library (its own NCCL
+communicator, kernel and ncclAllGather on one stream: pqb200_permanent_nccl); `permanent_distributed`
+uses the caller's torch.distributed group instead (NCCL on GPUs; gloo in the CPU tests) around
+pqb200_permanent_shard / pqb200_permanent_combine.
 
 The reference has no counterpart for splitting ONE permanent (its optional MPI mode shards shots,
 CGeneralizedCliffordsBSimulationStrategy.cpp:158-231); the partition mirrors what its TBB chunking
@@ -35,6 +37,50 @@ def gpu_shard_fn(a, rank, world, device, d_out=None, stream=None):
         None if d_out is None else ctypes.c_void_p(d_out),
         None if stream is None else ctypes.c_void_p(stream)))
     return host
+
+
+def _point_at_bundled_nccl():
+    """If the pip-bundled NCCL (the one torch links) is installed, make the library dlopen THAT file:
+    two NCCL builds with the same soname cannot live in one process, whichever is loaded first."""
+    import importlib.util
+    import os
+    if os.environ.get("PQB200_NCCL_LIB"):
+        return
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(base, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            os.environ["PQB200_NCCL_LIB"] = cand
+            return
+
+
+def nccl_init(rank, world, device, broadcast):
+    """Create the library's own NCCL communicator (pqb200_nccl_init).  `broadcast(bytes_or_None) ->
+    bytes` must hand rank 0's 128-byte id to every rank (MPI_Bcast, torch.distributed, a file ...)."""
+    lib = _lib.load()
+    _point_at_bundled_nccl()
+    buf = ctypes.create_string_buffer(128)
+    if rank == 0:
+        _lib.check(lib.pqb200_nccl_unique_id(buf))
+    ident = broadcast(buf.raw if rank == 0 else None)
+    _lib.check(lib.pqb200_nccl_init(device, rank, world, ctypes.create_string_buffer(bytes(ident), 128)))
+
+
+def nccl_shutdown():
+    _lib.check(_lib.load().pqb200_nccl_shutdown())
+
+
+def permanent_nccl(a):
+    """perm(a), collectively over the ranks of the library's communicator: shard kernel + ONE
+    ncclAllGather of 4 doubles per rank on the same stream, double-double fold on every rank."""
+    a = _lib.as_matrix(a)
+    out = np.zeros(2)
+    _lib.check(_lib.load().pqb200_permanent_nccl(_lib.dptr(a), a.shape[0], a.shape[1],
+                                                 a.strides[0] // 16, _lib.dptr(out)))
+    return complex(out[0], out[1])
 
 
 def permanent_distributed(a, group=None, device=None, shard_fn=None):

@@ -29,7 +29,9 @@ int main() {
         batch.reserve_space(1);
         batch.add(&in, &out, 0);
         std::vector<pqb200::Complex16> b = batch.calculate();
-        std::vector<double> pmf = pqb200::compute_pmf(m, out, in);
+        pic::PicState_int64 sample(2);  // one photon placed so far; compute_pmf adds the second
+        sample[0] = 1; sample[1] = 0;
+        std::vector<double> pmf = pqb200::compute_pmf(m, sample, in);
         std::printf("repeated=(%.15g,%.15g) plain=(%.15g,%.15g) glynn=(%.15g,%.15g) batch=(%.15g,%.15g) pmf0=%.6g\n",
                     v.real(), v.imag(), w.real(), w.imag(), g.real(), g.imag(), b[0].real(), b[0].imag(), pmf[0]);
         if (std::abs(v - pic::Complex16(-1, 0)) > 1e-14 || std::abs(b[0] - v) > 1e-14 || std::abs(w - g) > 1e-15)
