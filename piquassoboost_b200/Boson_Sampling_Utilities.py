@@ -105,7 +105,14 @@ class GlynnPermanentCalculator_wrapper:
             if self.lib in (GlynnSingleDFE, GlynnDualDFE, GlynnSingleDFEF, GlynnDualDFEF):
                 raise Pqb200Error("DFE (FPGA) permanent calculators are not part of this build")
             if self.lib == GlynnInf:
-                raise Pqb200Error("MPFR Not included")  # BBFGPermanentCalculator.cpp:100-107
+                # the reference's "Inf" calculators need an MPFR build (BBFGPermanentCalculator.cpp:100-107);
+                # here the request is served by the extended mode: every operation in double-double
+                # (~106 bits, pqb200_permanent_dd), for square matrices
+                if self._matrix is None:
+                    raise Pqb200Error("matrix is not set")
+                mats = self._matrix if isinstance(self._matrix, list) else [self._matrix]
+                vals = [permanent_double_double(m, self.ndev)[0] for m in mats]
+                return vals if isinstance(self._matrix, list) else vals[0]
             raise Pqb200Error("Wrong value set for permanent library.")
         if self._matrix is None:
             raise Pqb200Error("matrix is not set")
@@ -229,7 +236,7 @@ def _plain_class(name, lib, doc):
 
 
 GlynnPermanent = _plain_class("GlynnPermanent", GlynnRep, "Boson_Sampling_Utilities.py:206-216 (lib 0)")
-GlynnPermanentInf = _plain_class("GlynnPermanentInf", GlynnInf, "Boson_Sampling_Utilities.py:218-228 (lib 1; raises: no MPFR)")
+GlynnPermanentInf = _plain_class("GlynnPermanentInf", GlynnInf, "Boson_Sampling_Utilities.py:218-228 (lib 1; served by the double-double mode instead of MPFR)")
 GlynnPermanentDouble = _plain_class("GlynnPermanentDouble", GlynnDouble, "Boson_Sampling_Utilities.py:265-275 (lib 6)")
 BBFGPermanentDouble = _plain_class("BBFGPermanentDouble", BBFGDouble, "Boson_Sampling_Utilities.py:282-292 (lib 7)")
 BBFGPermanentLongDouble = _plain_class("BBFGPermanentLongDouble", BBFGLongDouble, "Boson_Sampling_Utilities.py:296-307 (lib 8)")

@@ -118,7 +118,15 @@ def test_errors_are_raised_not_swallowed(pqb):
     with pytest.raises(Exception):
         pqb.GlynnPermanentCalculator_wrapper(np.eye(3), 3).calculate()    # DFE id
     with pytest.raises(Exception):
-        pqb.GlynnPermanentInf(np.eye(3)).calculate()                      # MPFR id
+        pqb.GlynnRepeatedInfPermanentCalculator(np.eye(3), [1, 1, 1], [1, 1, 1]).calculate()  # MPFR id
+
+
+def test_inf_request_is_served_by_the_double_double_mode(pqb, ref):
+    """lib 1 (GlynnInf: MPFR in the reference, BBFGPermanentCalculator.cpp:100-107) -> pqb200_permanent_dd."""
+    A = haar_unitary(14, 141)
+    assert relerr(pqb.GlynnPermanentInf(A).calculate(), ref.bbfg(A, True)) < 1e-15
+    vals = pqb.GlynnPermanentCalculator_wrapper([A, A[:9, :9]], 1).calculate()
+    assert relerr(vals[1], ref.bbfg(np.ascontiguousarray(A[:9, :9]), True)) < 1e-15
 
 
 @pytest.mark.parametrize("L", [2, 3, 4, 5, 7, 9, 10])
