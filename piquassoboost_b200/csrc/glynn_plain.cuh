@@ -35,6 +35,7 @@
 
 #include "dd.cuh"
 #include "launch.h"
+#include "plain_host.h"
 
 namespace pqb200 {
 
@@ -42,7 +43,7 @@ constexpr int kPlainMaxN = 45;  // 16*N*N + header must fit the 32764-byte kerne
 
 template <int N>
 struct PlainParams {
-    double2 A2[N][N];  // 2*a[i][j] (exact doubling), rows x N used
+    double2 A2[N][plain_row_stride(N)];  // 2*a[i][j] (exact doubling), rows x N used
     int rows;          // n, 2 <= rows <= N
     int L;             // log2(chunk length), 1 <= L <= rows-1
     int K;             // log2(sub-chunk length), 1 <= K <= L: the column sums are re-derived from a
@@ -174,11 +175,11 @@ __device__ __forceinline__ void cmul(double& xr, double& xi, double yr, double y
 //   unroll 2   : rolled kernel (glynn_plain_rolled_kernel), best when the column sums alone take
 //                >= 136 registers;   unroll 4 / 8 : terms per iteration of glynn_plain_kernel.
 __host__ __device__ constexpr int default_unroll(int n) {
-    return n == 32 ? 8 : n >= 27 ? 2 : (n >= 17 && n <= 22) ? 4 : 8;
+    return n >= 27 ? 2 : (n >= 17 && n <= 22) ? 4 : 8;
 }
 __host__ __device__ constexpr int default_chains(int n) {
     return n >= 45 ? 2 : n == 44 ? 4 : n == 43 ? 4 : n == 42 ? 2 : n == 41 ? 4 : n == 40 ? 4 : n == 39 ? 2
-         : n == 38 ? 4 : n == 37 ? 8 : n == 36 ? 8 : n == 35 ? 4 : n == 34 ? 6 : n == 33 ? 6 : n == 32 ? 4
+         : n == 38 ? 4 : n == 37 ? 8 : n == 36 ? 8 : n == 35 ? 4 : n == 34 ? 6 : n == 33 ? 6 : n == 32 ? 7
          : n == 31 ? 7 : n == 30 ? 8 : n == 29 ? 7 : n == 28 ? 7 : n == 27 ? 8 : n == 26 ? 2 : n == 25 ? 2
          : n == 24 ? 8 : n == 23 ? 4 : n >= 17 ? 2 : n >= 8 ? 4 : n >= 4 ? 2 : 1;
 }

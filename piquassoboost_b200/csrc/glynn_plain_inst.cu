@@ -37,8 +37,9 @@ static cudaError_t launch_plain_n(const PlainLaunchArgs& x) {
     }
     PlainParams<N> p;
     const int rows = (int)x.rows, cols = (int)x.cols;
-    static_assert(sizeof(p.A2) == sizeof(double) * 2 * N * N, "A2 layout");
-    plain_normalise(x.a, rows, cols, x.stride, N, reinterpret_cast<double*>(&p.A2[0][0]), p.phase);
+    static_assert(sizeof(p.A2) == sizeof(double) * 2 * N * plain_row_stride(N), "A2 layout");
+    plain_normalise(x.a, rows, cols, x.stride, N, reinterpret_cast<double*>(&p.A2[0][0]), p.phase,
+                    plain_row_stride(N));
     p.rows = rows;
     p.L = x.L;
     p.K = x.K;

@@ -30,8 +30,16 @@ inline int plain_kernel_cols(int rows, int cols) {
 // a: rows x cols interleaved complex (stride in complex elements).  Writes the N x N (row-major,
 // interleaved re,im) pre-doubled, normalised matrix in the kernel's row order to a2 (N = plain_kernel_cols(rows, cols)) and the
 // dd complex correction factor to phase[4] = {re.hi, re.lo, im.hi, im.lo}.
+// row stride (complex elements) of the kernel's matrix: rows that are a multiple of 256 bytes apart
+// (N = 16, 32) are measurably slower through the constant path (all toggled rows alias), so those get
+// one padding element
+// (measured: N=32 26.5 -> 23.2 ms per 2^31 steps with the padding; no effect for other N)
+constexpr int plain_row_stride(int n) { return n % 16 == 0 ? n + 1 : n; }
+
+// ld: row stride of a2 in complex elements (0 = N)
 inline void plain_normalise(const double* a, int rows, int cols, size_t stride, int N, double* a2,
-                            double phase[4]) {
+                            double phase[4], int ld = 0) {
+    if (ld == 0) ld = N;
     typedef std::complex<long double> cld;
     std::vector<cld> b((size_t)N * N, cld(0.0L, 0.0L));
     for (int i = 0; i < rows; i++)
@@ -64,16 +72,16 @@ inline void plain_normalise(const double* a, int rows, int cols, size_t stride, 
     }
     // kernel row order: index k < rows-1 holds the row toggled by Gray bit k, i.e. matrix row
     // rows-1-k (index 0 = the real row); index rows-1 holds matrix row 0, whose delta is fixed to +1
-    for (size_t k = 0; k < (size_t)2 * N * N; k++) a2[k] = 0.0;
+    for (size_t k = 0; k < (size_t)2 * N * ld; k++) a2[k] = 0.0;
     for (int i = 0; i < rows; i++) {
         const int dst = i == 0 ? rows - 1 : rows - 1 - i;
         for (int j = 0; j < N; j++) {
-            a2[2 * ((size_t)dst * N + j)] = (double)(2.0L * b[(size_t)i * N + j].real());
-            a2[2 * ((size_t)dst * N + j) + 1] = (double)(2.0L * b[(size_t)i * N + j].imag());
+            a2[2 * ((size_t)dst * ld + j)] = (double)(2.0L * b[(size_t)i * N + j].real());
+            a2[2 * ((size_t)dst * ld + j) + 1] = (double)(2.0L * b[(size_t)i * N + j].imag());
         }
     }
     // the kernel relies on exact zeros here
-    for (int i = 0; i < N; i++) a2[2 * ((size_t)i * N + (N - 1)) + 1] = 0.0;
+    for (int i = 0; i < N; i++) a2[2 * ((size_t)i * ld + (N - 1)) + 1] = 0.0;
     for (int j = 0; j < N; j++) a2[2 * (size_t)j + 1] = 0.0;
     const double rh = (double)corr.real(), ih = (double)corr.imag();
     phase[0] = rh;

@@ -198,3 +198,30 @@ def test_large_haar_unitary_vs_committed_double_double(pqb, n, tol):
     assert relerr(got, want) < tol, (n, got, want)
     if "ref_long_double" in gold:
         assert relerr(got, complex(*gold["ref_long_double"])) < tol
+
+
+def test_concurrent_callers(pqb, ref):
+    """The reference's calculators are called concurrently from TBB workers
+    (samplingHelperFunctions.cpp:137, BatchedPermanentCalculator.cpp:343): the C ABI must be re-entrant
+    (one mutex inside the library serialises the launches; results must not mix)."""
+    import threading
+    mats = [haar_unitary(n, 300 + n) for n in (5, 9, 12, 14, 15, 10, 7, 13)]
+    want = [ref.bbfg(m, True) for m in mats]
+    got = [None] * len(mats)
+    errs = []
+
+    def work(k):
+        try:
+            for _ in range(20):
+                got[k] = pqb.GlynnPermanent(mats[k]).calculate()
+                if relerr(got[k], want[k]) > TOL:
+                    errs.append((k, got[k], want[k]))
+        except Exception as e:  # noqa: BLE001
+            errs.append((k, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(mats))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs, errs[:3]

@@ -25,7 +25,7 @@ struct Kern<N, CH, 2> { static constexpr auto fn = glynn_plain_rolled_kernel<N, 
 template <int N, int CH, int U>
 void run_variant(const std::vector<double>& A, int L, unsigned long long nchunks, double* partials, unsigned int* counter, double* out) {
     static PlainParams<N> p;
-    plain_normalise(A.data(), N, N, N, N, reinterpret_cast<double*>(&p.A2[0][0]), p.phase);
+    plain_normalise(A.data(), N, N, N, N, reinterpret_cast<double*>(&p.A2[0][0]), p.phase, plain_row_stride(N));
     CK(cudaFuncSetAttribute(Kern<N, CH, U>::fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plain_anchor_bytes<N>()));
     int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, Kern<N, CH, U>::fn, 256, plain_anchor_bytes<N>()));
     int grid = 148 * occ;
