@@ -45,7 +45,9 @@ constexpr int kRepMaxDigits = 44;
 
 // steps per chunk that fit the parameter space next to the N x N matrix (10 bytes per step)
 __host__ __device__ constexpr int rep_len_max(int n) {
-    return (32764 - 16 * n * n - 704) / 10 > 4096 ? 4096 : (32764 - 16 * n * n - 704) / 10;
+    return (32764 - 16 * n * plain_row_stride(n) - 704) / 10 > 4096
+               ? 4096
+               : (32764 - 16 * n * plain_row_stride(n) - 704) / 10;
 }
 
 // step-table entry and plain product used by the shared-memory kernels (glynn_batch.cuh,
@@ -84,7 +86,7 @@ __device__ __forceinline__ void term_prod(const double (&cr)[N], const double (&
 
 template <int N>
 struct RepParams {
-    double2 A2[N][N];  // 2*a, row 0 = anchor, rows 1..D = digit rows, columns physically repeated
+    double2 A2[N][plain_row_stride(N)];  // 2*a, row 0 = anchor, rows 1..D = digit rows, columns physically repeated
     // per local step t of a chunk:  w[t] = (-1)^t * prod_{low digits} C(r_d, k_d(t));
     // rf[t] = row toggled going INTO step t (1..D) | flags << 8, flag bit P: k increases (column
     // sums -= 2a) for a thread with high parity P.  rf[len] is a harmless dummy (row 1).

@@ -34,7 +34,12 @@ inline int plain_kernel_cols(int rows, int cols) {
 // (N = 16, 32) are measurably slower through the constant path (all toggled rows alias), so those get
 // one padding element
 // (measured: N=32 26.5 -> 23.2 ms per 2^31 steps with the padding; no effect for other N)
-constexpr int plain_row_stride(int n) { return n % 16 == 0 ? n + 1 : n; }
+#ifdef __CUDACC__
+#define PQB_HOST_DEVICE __host__ __device__
+#else
+#define PQB_HOST_DEVICE
+#endif
+PQB_HOST_DEVICE constexpr int plain_row_stride(int n) { return n % 16 == 0 ? n + 1 : n; }
 
 // ld: row stride of a2 in complex elements (0 = N)
 inline void plain_normalise(const double* a, int rows, int cols, size_t stride, int N, double* a2,

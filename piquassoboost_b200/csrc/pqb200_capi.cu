@@ -57,7 +57,7 @@ namespace {
 
 // keep in sync with rep_len_max() in glynn_repeated.cuh (steps per chunk that fit the parameter space)
 inline int rep_len_max_host(int n) {
-    const int v = (32764 - 16 * n * n - 704) / 10;
+    const int v = (32764 - 16 * n * plain_row_stride(n) - 704) / 10;
     return v > 4096 ? 4096 : v;
 }
 
