@@ -6,25 +6,30 @@
 //     colsum_j(g) = a_0j + sum_{i>=1} delta_i(g) a_ij,  delta_i = -1 iff bit (n-1-i) of g^(g>>1) is set
 //
 // How it is laid out on the GPU (this is not the reference's TBB chunking):
-//   * the 2^(n-1) Gray indices are cut into aligned chunks of 2^L steps; a THREAD owns a chunk, seeds
-//     its N complex column sums from the chunk's start code (this bounds the rounding drift of the
-//     running sums to 2^L updates) and keeps them in registers for the whole chunk;
-//   * because chunks are 2^L aligned, every thread of the grid toggles the SAME row at the same
-//     local step.  The whole matrix (pre-doubled, 2*a_ij) travels in the kernel-parameter constant
-//     bank and the toggled row is read with warp-uniform constant loads (LDCU) straight into uniform
-//     registers that feed the FP64 pipe as operands: no shared memory, no LSU traffic, no vector
-//     registers spent on row data.  All loops have warp-uniform trip counts so that the compiler
-//     can keep the row index in the uniform datapath; threads past the end of the chunk range run
-//     a dummy chunk whose sum is discarded;
+//   * the 2^(n-1) Gray indices are cut into aligned chunks of 2^L steps; a THREAD owns a chunk and
+//     keeps its N complex column sums in registers.  The sums are fully re-seeded from the chunk's
+//     start code and, every 2^K steps, re-derived from a per-thread anchor in shared memory ("two-level
+//     re-seeding" below): rounding drift of the running sums is the dominant error term;
+//   * because chunks are aligned, every thread of the grid toggles the SAME row at the same local
+//     step.  The whole matrix (pre-doubled, 2*a_ij; row k = the row toggled by Gray bit k, the
+//     delta=+1 row last) travels in the kernel-parameter constant bank and the toggled row is read
+//     with warp-uniform constant loads (LDCU) straight into uniform registers that feed the FP64
+//     pipe as operands: no LSU traffic, no vector registers spent on row data.  Loop counters, row
+//     indices and directions are functions of the local step only, so that they stay in the uniform
+//     datapath; threads past the end of the chunk range run a dummy chunk whose sum is discarded;
 //   * the host normalises the matrix with unit-modulus row/column factors (plain_host.h) so that the
-//     LAST ROW (the row the Gray code toggles at every second step) and the LAST COLUMN are real:
-//     the fast toggle then updates real parts only (N DADD instead of 2N) and the last factor of the
-//     product is a real number fused into the accumulate (2 DFMA).  The unit-modulus correction
-//     factor is applied once, in double-double, by the CTA that finishes the grid reduction;
+//     row of Gray bit 0 (toggled at every second step) and the LAST COLUMN are real: the fast toggle
+//     then updates real parts only (N instead of 2N adds) and the last factor of the product is a real
+//     number fused into the accumulate (2 DFMA).  The correction factor is applied once, in
+//     double-double, by the CTA that finishes the grid reduction;
 //   * per step: (N + 2N-1)/2 DFMA (column update, averaged over fast/general toggles) + 4(N-2) + 2
 //     DMUL/DFMA (complex product chains) = 5.5N-6.5 FP64 instructions for 8N algorithmic flops
-//     (a straight complex evaluation needs 6N-4);
-//   * every DDP (default 8) terms the partial sum is folded into a double-double accumulator (TwoSum), chunk sums
+//     (a straight complex evaluation needs 6N-4).  Every term is fused with the toggle into the next
+//     one (term_toggle) so that independent updates sit between the dependent multiplies;
+//   * two loop forms, chosen per N by measurement (default_unroll / default_chains):
+//     glynn_plain_kernel (8 or 4 terms per iteration, compile-time rows and directions) and
+//     glynn_plain_rolled_kernel (a pair of terms per iteration, run-time row index);
+//   * every 8 terms the partial sum is folded into a double-double accumulator (TwoSum); chunk sums
 //     are combined per thread in dd, then warp shuffle -> shared -> one partial per CTA -> the last
 //     CTA reduces all partials in a fixed order (deterministic) into 4 doubles (re.hi re.lo im.hi
 //     im.lo);
