@@ -478,8 +478,8 @@ glynn_plain_kernel(const __grid_constant__ PlainParams<N> p) {
 // run-time row for the second toggle).  ptxas schedules this form better than the unrolled one when
 // the column sums alone take ~160 registers (N >= 35); which form serves which N is decided by
 // measurement (tools/microbench/tune_plain.cu -> default_unroll).
-template <int N, int CH = default_chains(N)>
-__global__ void __launch_bounds__(kPlainThreads, 1)
+template <int N, int CH = default_chains(N), int MINB = 1>
+__global__ void __launch_bounds__(kPlainThreads, MINB)
 glynn_plain_rolled_kernel(const __grid_constant__ PlainParams<N> p) {
     const int L = p.L, K = p.K;
     const unsigned int nsteps = 1u << K;        // steps per sub-chunk

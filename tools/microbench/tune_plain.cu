@@ -21,6 +21,8 @@ template <int N, int CH, int U>
 struct Kern { static constexpr auto fn = glynn_plain_kernel<N, CH, U>; };
 template <int N, int CH>
 struct Kern<N, CH, 2> { static constexpr auto fn = glynn_plain_rolled_kernel<N, CH>; };
+template <int N, int CH>
+struct Kern<N, CH, 22> { static constexpr auto fn = glynn_plain_rolled_kernel<N, CH, 2>; };  // 2 CTAs/SM
 
 template <int N, int CH, int U>
 void run_variant(const std::vector<double>& A, int L, unsigned long long nchunks, double* partials, unsigned int* counter, double* out) {
@@ -52,13 +54,20 @@ template <int N>
 void sweep() {
     const int L = N - 1 < 12 ? N - 1 : 12;
     // ~2^31 steps for big N; everything for small N
-    const int lg = N - 1 < 31 ? N - 1 : 31;
+    // always 2^31 steps: for small N the chunk range simply revisits the Gray space (throughput test)
+    const int lg = 31;
     const unsigned long long nchunks = 1ull << (lg - L);
     std::mt19937_64 rng(N); std::normal_distribution<double> nd(0, 1);
     std::vector<double> A(2 * N * N);
     for (auto& z : A) z = nd(rng) * std::sqrt(0.5 / N);
     double* partials; unsigned int* counter; double* out;
     CK(cudaMalloc(&partials, 4 * 8 * 4096)); CK(cudaMalloc(&counter, 4)); CK(cudaMemset(counter, 0, 4)); CK(cudaMalloc(&out, 32));
+#ifdef TWO_CTA
+    run_variant<N, 2, 22>(A, L, nchunks, partials, counter, out);
+    run_variant<N, 3, 22>(A, L, nchunks, partials, counter, out);
+    run_variant<N, 4, 22>(A, L, nchunks, partials, counter, out);
+    run_variant<N, 6, 22>(A, L, nchunks, partials, counter, out);
+#endif
     run_variant<N, 2, 2>(A, L, nchunks, partials, counter, out);
     run_variant<N, 3, 2>(A, L, nchunks, partials, counter, out);
     run_variant<N, 4, 2>(A, L, nchunks, partials, counter, out);
