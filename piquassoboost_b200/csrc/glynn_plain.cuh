@@ -174,19 +174,16 @@ __device__ __forceinline__ void cmul(double& xr, double& xi, double yr, double y
 }
 
 // Loop form and multiply-chain count per N: the argmin of the measured sweep
-// tools/microbench/tune_plain.cu on B200 (profiles/tune_plain_r1.log).  The FP64 pipe only stays fed
+// tools/microbench/tune_plain.cu on B200 (profiles/tune_plain_final_r1.log).  The FP64 pipe only stays fed
 // if ptxas interleaves the dependent multiply chains with the independent column updates, and how
 // well it does that depends on N (register pressure) -- so the choice is tabulated, not modelled.
 //   unroll 2   : rolled kernel (glynn_plain_rolled_kernel), best when the column sums alone take
 //                >= 136 registers;   unroll 4 / 8 : terms per iteration of glynn_plain_kernel.
-__host__ __device__ constexpr int default_unroll(int n) {
-    return n >= 27 ? 2 : (n >= 17 && n <= 22) ? 4 : 8;
-}
+__host__ __device__ constexpr int default_unroll(int n) { return n >= 27 ? 2 : n == 16 ? 4 : 8; }
 __host__ __device__ constexpr int default_chains(int n) {
-    return n >= 45 ? 2 : n == 44 ? 4 : n == 43 ? 4 : n == 42 ? 2 : n == 41 ? 4 : n == 40 ? 4 : n == 39 ? 2
-         : n == 38 ? 4 : n == 37 ? 8 : n == 36 ? 8 : n == 35 ? 4 : n == 34 ? 6 : n == 33 ? 6 : n == 32 ? 7
-         : n == 31 ? 7 : n == 30 ? 8 : n == 29 ? 7 : n == 28 ? 7 : n == 27 ? 8 : n == 26 ? 2 : n == 25 ? 2
-         : n == 24 ? 8 : n == 23 ? 4 : n >= 17 ? 2 : n >= 8 ? 4 : n >= 4 ? 2 : 1;
+    //                    n = 0  1  2  3  4  5  6  7  8 ...                      (profiles/tune_plain_final_r1.log)
+    constexpr int t[46] = {1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 2, 8, 3, 2, 8, 2, 6, 6, 4, 2, 8, 2, 4, 8, 6, 6, 8, 7, 8, 7, 6, 8, 8, 7, 8, 7, 2, 6, 4, 7, 6, 6, 3, 4, 5};
+    return t[n < 0 ? 0 : n > 45 ? 45 : n];
 }
 
 // column update  x <- x + sign * a   with  SIGNMODE 0: sign = +1 and 1: sign = -1 at compile time (DADD
@@ -194,6 +191,15 @@ __host__ __device__ constexpr int default_chains(int n) {
 template <int SIGNMODE>
 __device__ __forceinline__ double upd(double x, double a, double sg) {
     return SIGNMODE == 0 ? x + a : SIGNMODE == 1 ? x - a : fma(sg, a, x);
+}
+
+// Real part of element j of row `row`.  The real row (index 0, Gray bit 0) is stored COMPACTLY: its N
+// real parts are the first N doubles of the row, so that one LDCU.128 brings two of them (the row is
+// read at every second step; uniform-load bandwidth is a co-limiter of this kernel).
+template <int N, bool REALROW>
+__device__ __forceinline__ double row_re(const PlainParams<N>& p, int row, int j) {
+    if (REALROW) return reinterpret_cast<const double*>(&p.A2[row][0])[j];
+    return p.A2[row][j].x;
 }
 
 // One Gray term, acc += (NEG ? -1 : +1) * prod_j c[j], fused with the toggle of row `row` into the
@@ -212,13 +218,13 @@ __device__ __forceinline__ void term_toggle(const PlainParams<N>& p, int row, do
     for (int k = 0; k < C; k++) {
         qr[k] = cr[k];
         qi[k] = ci[k];
-        cr[k] = upd<SIGNMODE>(cr[k], p.A2[row][k].x, sg);
+        cr[k] = upd<SIGNMODE>(cr[k], row_re<N, REALROW>(p, row, k), sg);
         if (!REALROW) ci[k] = upd<SIGNMODE>(ci[k], p.A2[row][k].y, sg);
     }
 #pragma unroll
     for (int j = C; j < M; j++) {
         cmul(qr[j % C], qi[j % C], cr[j], ci[j]);
-        cr[j] = upd<SIGNMODE>(cr[j], p.A2[row][j].x, sg);
+        cr[j] = upd<SIGNMODE>(cr[j], row_re<N, REALROW>(p, row, j), sg);
         if (!REALROW) ci[j] = upd<SIGNMODE>(ci[j], p.A2[row][j].y, sg);
     }
 #pragma unroll
@@ -227,12 +233,12 @@ __device__ __forceinline__ void term_toggle(const PlainParams<N>& p, int row, do
         for (int k = 0; k + w < C; k += 2 * w) cmul(qr[k], qi[k], qr[k + w], qi[k + w]);
     }
     const double f = NEG ? -cr[N - 1] : cr[N - 1];
-    cr[N - 1] = upd<SIGNMODE>(cr[N - 1], p.A2[row][N - 1].x, sg);
+    cr[N - 1] = upd<SIGNMODE>(cr[N - 1], row_re<N, REALROW>(p, row, N - 1), sg);
     acc_re = fma(qr[0], f, acc_re);
     acc_im = fma(qi[0], f, acc_im);
 }
 
-// c += sg * row (seeding and the rare mid-chunk correction)
+// c += sg * row (seeding and the rare mid-chunk correction); row >= 1 (row 0 is stored compactly)
 template <int N>
 __device__ __forceinline__ void toggle_row(const PlainParams<N>& p, int row, double sg,
                                            double (&cr)[N], double (&ci)[N]) {
@@ -356,8 +362,13 @@ __device__ __forceinline__ void subchunk_start(const PlainParams<N>& p, double* 
             cr[j] = 0.5 * p.A2[rows - 1][j].x;
             if (j < N - 1) ci[j] = 0.5 * p.A2[rows - 1][j].y;
         }
+        {
+            const double d = (gray0 & 1ull) ? -0.5 : 0.5;  // Gray bit 0: the compact real row
+#pragma unroll
+            for (int j = 0; j < N; j++) cr[j] = fma(d, row_re<N, true>(p, 0, j), cr[j]);
+        }
 #pragma unroll 1
-        for (int k = 0; k < rows - 1; k++) {
+        for (int k = 1; k < rows - 1; k++) {
             const double d = ((gray0 >> k) & 1ull) ? -0.5 : 0.5;
             toggle_row<N>(p, k, d, cr, ci);
         }

@@ -85,9 +85,14 @@ inline void plain_normalise(const double* a, int rows, int cols, size_t stride, 
             a2[2 * ((size_t)dst * ld + j) + 1] = (double)(2.0L * b[(size_t)i * N + j].imag());
         }
     }
-    // the kernel relies on exact zeros here
+    // the kernel relies on exact zeros in the imaginary parts of the last column ...
     for (int i = 0; i < N; i++) a2[2 * ((size_t)i * ld + (N - 1)) + 1] = 0.0;
-    for (int j = 0; j < N; j++) a2[2 * (size_t)j + 1] = 0.0;
+    // ... and reads the real row (index 0) COMPACTLY: its N real parts are the first N doubles of the row
+    if (rows >= 2) {
+        std::vector<double> re((size_t)N);
+        for (int j = 0; j < N; j++) re[j] = a2[2 * (size_t)j];
+        for (int j = 0; j < 2 * N; j++) a2[j] = j < N ? re[j] : 0.0;
+    }
     const double rh = (double)corr.real(), ih = (double)corr.imag();
     phase[0] = rh;
     phase[1] = (double)(corr.real() - (long double)rh);
