@@ -281,7 +281,7 @@ def run_b200(args, rank, local_rank, world):
             "parity_check": {"n": 18, "rel_err_vs_long_double_reference": abs(got - want) / abs(want),
                              "tolerance": 1e-10},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tflops, "traffic": 223232,
+                         "frac": achieved / peak_tflops, "traffic": 80896,
                          "peak_source": "measured live: pqb200_fp64_peak DFMA chains x 2 flop "
                                         f"(DADD-only issue rate {dadd.value / 1e12:.2f} T thread-instr/s; "
                                         "nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2)",
