@@ -225,3 +225,16 @@ def test_concurrent_callers(pqb, ref):
     for t in threads:
         t.join()
     assert not errs, errs[:3]
+
+
+def test_block_diagonal_n42_full_size(pqb, ref):
+    """A full-size run beyond n=40 with a known answer: perm(A (+) B) = perm(A) perm(B) for two 21x21
+    Haar blocks (identity (ii)); 2^41 Gray steps (~30 s on one B200).  The zero
+    blocks also put exact zeros into the row / column that the normalisation makes real."""
+    A, B = haar_unitary(21, 2101), haar_unitary(21, 2102)
+    M = np.zeros((42, 42), dtype=complex)
+    M[:21, :21] = A
+    M[21:, 21:] = B
+    want = ref.bbfg(A, True) * ref.bbfg(B, True)
+    got = pqb.GlynnPermanent(M).calculate()
+    assert relerr(got, want) < 1e-10, (got, want)
