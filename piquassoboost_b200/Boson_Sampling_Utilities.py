@@ -132,7 +132,7 @@ class GlynnPermanentCalculator_wrapper:
         out = np.zeros(2 * n, dtype=np.float64)
         _lib.check(lib.pqb200_permanent_batch(ptrs, rows, cols, strides, n, self.ndev,
                                               _lib.dptr(out)))
-        return [complex(out[2 * k], out[2 * k + 1]) for k in range(n)]
+        return out.view(np.complex128).tolist()
 
 
 class ChinHuhPermanentCalculator_wrapper:
@@ -176,14 +176,17 @@ class ChinHuhPermanentCalculator_wrapper:
         count = len(ins) * len(outs)
         if count == 0:
             return [[] for _ in ins]
-        rows = np.ascontiguousarray(np.stack([o for _ in ins for o in outs]), dtype=np.int64)
-        cols = np.ascontiguousarray(np.stack([i for i in ins for _ in outs]), dtype=np.int64)
+        # (input i, output o) pairs in row-major order; bulk numpy conversions -- for tens of thousands
+        # of tiny permanents the Python list handling, not the GPU, is the cost of this call
+        o = np.array(outs, dtype=np.int64).reshape(len(outs), -1)
+        i = np.array(ins, dtype=np.int64).reshape(len(ins), -1)
+        rows = np.ascontiguousarray(np.tile(o, (len(ins), 1)))
+        cols = np.ascontiguousarray(np.repeat(i, len(outs), axis=0))
         out = np.zeros(2 * count, dtype=np.float64)
         _lib.check(_lib.load().pqb200_permanent_repeated_batch(
             _lib.dptr(m), m.shape[0], m.shape[1], m.strides[0] // 16, _lib.iptr(rows),
             _lib.iptr(cols), count, self.ndev, _lib.dptr(out)))
-        vals = [complex(out[2 * k], out[2 * k + 1]) for k in range(count)]
-        return [vals[i * len(outs):(i + 1) * len(outs)] for i in range(len(ins))]
+        return out.view(np.complex128).reshape(len(ins), len(outs)).tolist()
 
 
 class RepeatedPermanentCalculator(ChinHuhPermanentCalculator_wrapper):
