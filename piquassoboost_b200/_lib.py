@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libpqb200.so")
+# PQB200_LIB: alternative build of the library (tuning experiments); default: the in-tree build
+_LIB_PATH = os.environ.get("PQB200_LIB") or os.path.join(_HERE, "libpqb200.so")
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int64_p = ctypes.POINTER(ctypes.c_int64)

@@ -141,7 +141,8 @@ __device__ __forceinline__ void rep_term_toggle(const RepParams<N>& p, int row, 
     acc_im = fma(qi[0], f, acc_im);
 }
 
-__host__ __device__ constexpr int rep_chains(int n) { return n >= 26 ? 4 : n >= 8 ? 4 : n >= 4 ? 2 : 1; }
+// measured on C4-shaped problems (tools/rep_cases.py): the chain count matters little (+-3 %)
+__host__ __device__ constexpr int rep_chains(int n) { return n >= 36 ? 4 : n >= 4 ? 2 : 1; }
 
 template <int N>
 __device__ __forceinline__ void rep_toggle(const RepParams<N>& p, int row, double sg,
