@@ -88,10 +88,14 @@ template <int N>
 struct RepParams {
     double2 A2[N][plain_row_stride(N)];  // 2*a, row 0 = anchor, rows 1..D = digit rows, columns physically repeated
     // per local step t of a chunk:  w[t] = (-1)^t * prod_{low digits} C(r_d, k_d(t));
-    // rf[t] = row toggled going INTO step t (1..D) | flags << 8, flag bit P: k increases (column
-    // sums -= 2a) for a thread with high parity P.  rf[len] is a harmless dummy (row 1).
+    // trow[t] = row toggled going INTO step t (1..D); tflags[t] bit P: k increases (column sums -= 2a)
+    // for a thread with high parity P.  Entry len is a harmless dummy (row 1).
     double w[rep_len_max(N) + 1];
-    unsigned short rf[rep_len_max(N) + 2];
+    // row index and direction flags in SEPARATE arrays: the row index must stay a uniform value (it
+    // addresses the row loads), the flags meet the per-thread parity P in vector code; one combined
+    // entry drags the row index -- and with it every row load -- onto the vector path (measured)
+    unsigned char trow[rep_len_max(N) + 2];
+    unsigned char tflags[rep_len_max(N) + 2];
     int D;             // number of digits (rows - 1)
     int q;             // number of low digits
     unsigned int len;  // steps per chunk = prod_{d<q} radix[d]
@@ -106,29 +110,38 @@ struct RepParams {
     unsigned int* counter;
     double* out;
     double phase[4];        // unit-modulus correction factor (dd complex) applied to the sum
+    int real_row;           // == 1, as a run-time value: with a literal row index ptxas hoists the whole
+                            // real row into uniform registers and pushes the step counter out of them
 };
 
 // One weighted term, acc += w * prod_j c[j], fused with the toggle of row `row` into the next term
 // (see term_toggle in glynn_plain.cuh).  REALROW: the toggled row is real (row 1).
+#ifndef PQB_REP_LAG
+#define PQB_REP_LAG 4
+#endif
+// The toggle of column j is issued PQB_REP_LAG columns behind the chain multiply that last used it: the
+// row index comes out of the step table (a uniform load), the row loads depend on it, and a warp issues in
+// order -- the first toggle must not sit at the top of the term.
 template <int N, int CH, bool REALROW>
 __device__ __forceinline__ void rep_term_toggle(const RepParams<N>& p, int row, double sg, double w,
                                                 double (&cr)[N], double (&ci)[N], double& acc_re,
                                                 double& acc_im) {
     constexpr int M = N - 1;  // complex factors; column N-1 is real
     constexpr int C = CH < M ? CH : M;
+    constexpr int LAG = PQB_REP_LAG;
     double qr[C], qi[C];
 #pragma unroll
     for (int k = 0; k < C; k++) {
         qr[k] = cr[k];
         qi[k] = ci[k];
-        cr[k] = fma(sg, p.A2[row][k].x, cr[k]);
-        if (!REALROW) ci[k] = fma(sg, p.A2[row][k].y, ci[k]);
     }
 #pragma unroll
     for (int j = C; j < M; j++) {
         cmul(qr[j % C], qi[j % C], cr[j], ci[j]);
-        cr[j] = fma(sg, p.A2[row][j].x, cr[j]);
-        if (!REALROW) ci[j] = fma(sg, p.A2[row][j].y, ci[j]);
+        if (j - LAG >= 0) {
+            cr[j - LAG] = fma(sg, p.A2[row][j - LAG].x, cr[j - LAG]);
+            if (!REALROW) ci[j - LAG] = fma(sg, p.A2[row][j - LAG].y, ci[j - LAG]);
+        }
     }
 #pragma unroll
     for (int v = 1; v < C; v *= 2) {
@@ -136,6 +149,11 @@ __device__ __forceinline__ void rep_term_toggle(const RepParams<N>& p, int row, 
         for (int k = 0; k + v < C; k += 2 * v) cmul(qr[k], qi[k], qr[k + v], qi[k + v]);
     }
     const double f = w * cr[N - 1];
+#pragma unroll
+    for (int j = (M - LAG > 0 ? M - LAG : 0); j < M; j++) {
+        cr[j] = fma(sg, p.A2[row][j].x, cr[j]);
+        if (!REALROW) ci[j] = fma(sg, p.A2[row][j].y, ci[j]);
+    }
     cr[N - 1] = fma(sg, p.A2[row][N - 1].x, cr[N - 1]);
     acc_re = fma(qr[0], f, acc_re);
     acc_im = fma(qi[0], f, acc_im);
@@ -206,11 +224,10 @@ glynn_repeated_kernel(const __grid_constant__ RepParams<N> p) {
 #pragma unroll 1
         for (unsigned int t = 0; t < len; t++) {
             const double w = p.w[t];
-            const unsigned int rf = p.rf[t + 1];
-            const int row = (int)(rf & 0xffu);
-            const double sg = ((rf >> (8 + P)) & 1u) ? -1.0 : 1.0;
+            const int row = (int)p.trow[t + 1];
+            const double sg = ((p.tflags[t + 1] >> P) & 1u) ? -1.0 : 1.0;
             if (row == 1)
-                rep_term_toggle<N, CH, true>(p, row, sg, w, cr, ci, bs_re, bs_im);
+                rep_term_toggle<N, CH, true>(p, p.real_row, sg, w, cr, ci, bs_re, bs_im);
             else
                 rep_term_toggle<N, CH, false>(p, row, sg, w, cr, ci, bs_re, bs_im);
             if ((t & 7u) == 7u) {  // fold into the double-double accumulator every 8 terms

@@ -41,11 +41,14 @@ static cudaError_t launch_rep_n(const RepLaunchArgs& x) {
     const RepStepHost* tab = (const RepStepHost*)x.table;
     for (unsigned int t = 0; t < x.len; t++) {
         p.w[t] = tab[t].w;
-        p.rf[t] = (unsigned short)((unsigned int)tab[t].row | (tab[t].flags << 8));
+        p.trow[t] = (unsigned char)tab[t].row;
+        p.tflags[t] = (unsigned char)tab[t].flags;
     }
-    p.rf[0] = 1;
+    p.trow[0] = 1;
     p.w[x.len] = 0.0;
-    p.rf[x.len] = 1;  // dummy toggle behind the last term of a chunk (row 1, never used)
+    p.trow[x.len] = 1;  // dummy toggle behind the last term of a chunk (row 1, never used)
+    p.tflags[x.len] = 0;
+    p.real_row = 1;
     p.base = (const double2*)x.base;
     p.binom = x.binom;
     p.low_parity[0] = x.low_parity[0];
