@@ -93,6 +93,15 @@ int pqb200_permanent_nccl_async(const double* a, size_t rows, size_t cols, size_
 int pqb200_permanent_dd(const double* a, size_t rows, size_t cols, size_t stride, int ndev,
                         double out_dd[4]);
 
+/* The repeated-row permanent with EVERY operation in double-double arithmetic: the counterpart of
+ *   BBFGPermanentCalculatorRepeated::calculate(mtx, col_mult, row_mult, use_extended=true / use_inf=true)
+ *                                                 sampling/source/BBFGPermanentCalculatorRepeated.cpp:105-141
+ * (long double / MPFR there).  Same argument meaning and edge semantics as pqb200_permanent_repeated;
+ * out_dd = re.hi re.lo im.hi im.lo.  Slow by design (a straight walk of the reference's n-ary Gray code). */
+int pqb200_permanent_repeated_dd(const double* a, size_t rows, size_t cols, size_t stride,
+                                 const int64_t* row_mult, const int64_t* col_mult, int ndev,
+                                 double out_dd[4]);
+
 /* Many plain permanents in one call: count matrices, matrix k is rows[k] x cols[k] with stride
  * strides[k].  Replaces the list-of-matrices branch of the Python wrapper
  * (sampling/GlynnPermanentCalculator_Wrapper.hpp:204-293). */

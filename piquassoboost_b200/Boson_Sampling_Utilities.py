@@ -162,7 +162,15 @@ class ChinHuhPermanentCalculator_wrapper:
                             GlynnRepMultiDualDFE, 10, 11):
                 raise Pqb200Error("DFE (FPGA) permanent calculators are not part of this build")
             if self.lib == GlynnRepInf:
-                raise Pqb200Error("MPFR Not included")
+                # the reference needs an MPFR build for this id (BBFGPermanentCalculatorRepeated.cpp:117-124);
+                # here it is served by the extended mode (every operation in double-double)
+                ins, outs = self.input_state, self.output_state
+                if isinstance(ins, list) or isinstance(outs, list):
+                    ins = ins if isinstance(ins, list) else [ins]
+                    outs = outs if isinstance(outs, list) else [outs]
+                    return [[permanent_repeated_double_double(self.matrix, i, o, self.ndev)[0] for o in outs]
+                            for i in ins]
+                return permanent_repeated_double_double(self.matrix, ins, outs, self.ndev)[0]
             raise Pqb200Error("Wrong value set for permanent library.")
         ins, outs = self.input_state, self.output_state
         if isinstance(ins, list) or isinstance(outs, list):
@@ -229,7 +237,7 @@ BBFGRepeatedPermanentCalculatorDouble = _repeated_class(
 BBFGRepeatedPermanentCalculatorLongDouble = _repeated_class(
     "BBFGRepeatedPermanentCalculatorLongDouble", BBFGRepLongDouble, "Boson_Sampling_Utilities.py:193-203 (lib 8)")
 GlynnRepeatedInfPermanentCalculator = _repeated_class(
-    "GlynnRepeatedInfPermanentCalculator", GlynnRepInf, "Boson_Sampling_Utilities.py:120-123 (lib 9; raises: no MPFR)")
+    "GlynnRepeatedInfPermanentCalculator", GlynnRepInf, "Boson_Sampling_Utilities.py:120-123 (lib 9; served by the double-double mode instead of MPFR)")
 
 
 def _plain_class(name, lib, doc):
@@ -267,4 +275,19 @@ def permanent_double_double(matrix, ndev=None):
     _lib.check(_lib.load().pqb200_permanent_dd(
         _lib.dptr(m), m.shape[0], m.shape[1], m.strides[0] // 16 if m.shape[1] else 0,
         DEFAULT_NDEV if ndev is None else int(ndev), _lib.dptr(parts)))
+    return complex(parts[0] + parts[1], parts[2] + parts[3]), parts
+
+
+def permanent_repeated_double_double(matrix, input_state, output_state, ndev=None):
+    """The repeated-row permanent with every operation in double-double arithmetic
+    (`pqb200_permanent_repeated_dd`).  Returns `(value, parts)` like `permanent_double_double`."""
+    m = _lib.as_matrix(matrix)
+    cols = _lib.as_state(input_state)
+    rows = _lib.as_state(output_state)
+    if len(cols) != m.shape[1] or len(rows) != m.shape[0]:
+        raise Pqb200Error("state lengths do not match the matrix shape")
+    parts = np.zeros(4, dtype=np.float64)
+    _lib.check(_lib.load().pqb200_permanent_repeated_dd(
+        _lib.dptr(m), m.shape[0], m.shape[1], m.strides[0] // 16 if m.shape[1] else 0,
+        _lib.iptr(rows), _lib.iptr(cols), DEFAULT_NDEV if ndev is None else int(ndev), _lib.dptr(parts)))
     return complex(parts[0] + parts[1], parts[2] + parts[3]), parts

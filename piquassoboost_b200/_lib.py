@@ -72,6 +72,11 @@ _SIGNATURES = {
         [c_double_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, c_int64_p, c_int64_p,
          ctypes.c_int, c_double_p],
     ),
+    "pqb200_permanent_repeated_dd": (
+        ctypes.c_int,
+        [c_double_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, c_int64_p, c_int64_p,
+         ctypes.c_int, c_double_p],
+    ),
     "pqb200_permanent_repeated_batch": (
         ctypes.c_int,
         [c_double_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, c_int64_p, c_int64_p,

@@ -48,6 +48,9 @@ PQB_DECL_REP_FILL(40)
 PQB_DECL_REP_FILL(43)
 
 namespace pqb200 {
+cudaError_t launch_repeated_dd(const double* d_mat, const double* d_binom, int D, int N, const int* r,
+                               unsigned long long begin, unsigned long long end, int max_blocks,
+                               double* partials, unsigned int* counter, double* out, cudaStream_t stream);
 cudaError_t launch_plain_dd(const double* d_a, int n, int L, unsigned long long cb, unsigned long long ce,
                             int grid, double* partials, unsigned int* counter, double* out,
                             cudaStream_t stream);
@@ -513,6 +516,86 @@ int pqb200_permanent_dd(const double* a, size_t rows, size_t cols, size_t stride
         cdd_add(tot, x);
     }
     const int e = -(n - 1);  // exact power-of-two scaling of both parts
+    out_dd[0] = ldexp(tot.re.hi, e);
+    out_dd[1] = ldexp(tot.re.lo, e);
+    out_dd[2] = ldexp(tot.im.hi, e);
+    out_dd[3] = ldexp(tot.im.lo, e);
+    return PQB200_OK;
+}
+
+int pqb200_permanent_repeated_dd(const double* a, size_t rows, size_t cols, size_t stride,
+                                 const int64_t* row_mult, const int64_t* col_mult, int ndev,
+                                 double out_dd[4]) {
+    if (!out_dd) return fail(PQB200_ERR_ARG, "output pointer is null");
+    if (!row_mult || !col_mult) return fail(PQB200_ERR_ARG, "multiplicity pointer is null");
+    if (rows != 0 && cols != 0) {
+        if (!a) return fail(PQB200_ERR_ARG, "matrix pointer is null");
+        if (stride < cols) return fail(PQB200_ERR_ARG, "stride is smaller than the number of columns");
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    int used = 0;
+    int rc = ensure_devices(ndev, &used);
+    if (rc) return rc;
+    RepPrepared pr;
+    std::string err;
+    rc = rep_prepare(a, rows, cols, stride, row_mult, col_mult, kMaxRepN, pr, err);
+    if (rc) return fail(rc, err);
+    out_dd[1] = out_dd[3] = 0.0;
+    if (pr.trivial) {
+        out_dd[0] = pr.value[0];
+        out_dd[2] = pr.value[1];
+        return PQB200_OK;
+    }
+    const int D = pr.R - 1, N = pr.N;
+    double total_d = 1.0;
+    unsigned long long total = 1;
+    for (int d = 0; d < D; d++) {
+        total_d *= (double)(pr.r[d] + 1);
+        total *= (unsigned long long)(pr.r[d] + 1);
+    }
+    if (total_d > 1.8e19) return fail(PQB200_ERR_ARG, "Gray space exceeds 2^64 steps");
+    std::vector<double> binom((size_t)std::max(D, 1) * kRepBinomStride, 0.0);
+    for (int d = 0; d < D; d++)
+        for (int k = 0; k <= pr.r[d]; k++) binom[(size_t)d * kRepBinomStride + k] = binom_d(pr.r[d], k);
+    if ((unsigned long long)used > total) used = (int)total;
+    std::vector<double*> d_mat((size_t)used, nullptr), d_bin((size_t)used, nullptr);
+    std::vector<double> parts(4 * (size_t)used);
+    g_stats = {0.0, total_d, (uint64_t)used, used};
+    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
+    CUDA_TRY(cudaEventRecord(g_devs[0].e0, g_devs[0].stream));
+    for (int d = 0; d < used; d++) {
+        DeviceCtx& c = g_devs[d];
+        CUDA_TRY(cudaSetDevice(c.dev));
+        CUDA_TRY(cudaMalloc(&d_mat[d], sizeof(double) * pr.mat.size()));
+        CUDA_TRY(cudaMalloc(&d_bin[d], sizeof(double) * binom.size()));
+        CUDA_TRY(cudaMemcpyAsync(d_mat[d], pr.mat.data(), sizeof(double) * pr.mat.size(), cudaMemcpyHostToDevice, c.stream));
+        CUDA_TRY(cudaMemcpyAsync(d_bin[d], binom.data(), sizeof(double) * binom.size(), cudaMemcpyHostToDevice, c.stream));
+        const unsigned long long b = (unsigned long long)((__uint128_t)total * (unsigned)d / (unsigned)used);
+        const unsigned long long e = (unsigned long long)((__uint128_t)total * (unsigned)(d + 1) / (unsigned)used);
+        CUDA_TRY(launch_repeated_dd(d_mat[d], d_bin[d], D, N, pr.r.data(), b, e, c.sm_count, c.partials,
+                                    c.counter, c.d_out, c.stream));
+        CUDA_TRY(cudaMemcpyAsync(c.h_out, c.d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        if (d == 0) CUDA_TRY(cudaEventRecord(c.e1, c.stream));
+    }
+    cdd tot = cdd_zero();
+    for (int d = 0; d < used; d++) {
+        DeviceCtx& c = g_devs[d];
+        CUDA_TRY(cudaSetDevice(c.dev));
+        CUDA_TRY(cudaStreamSynchronize(c.stream));
+        cdd x;
+        x.re.hi = c.h_out[0];
+        x.re.lo = c.h_out[1];
+        x.im.hi = c.h_out[2];
+        x.im.lo = c.h_out[3];
+        cdd_add(tot, x);
+        CUDA_TRY(cudaFree(d_mat[d]));
+        CUDA_TRY(cudaFree(d_bin[d]));
+    }
+    float ms = 0.f;
+    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
+    CUDA_TRY(cudaEventElapsedTime(&ms, g_devs[0].e0, g_devs[0].e1));
+    g_stats.kernel_ms = ms;
+    const int e = -(pr.photons - 1);
     out_dd[0] = ldexp(tot.re.hi, e);
     out_dd[1] = ldexp(tot.re.lo, e);
     out_dd[2] = ldexp(tot.im.hi, e);

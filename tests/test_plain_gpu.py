@@ -117,8 +117,6 @@ def test_errors_are_raised_not_swallowed(pqb):
         pqb.GlynnPermanent(np.ones((46, 46), dtype=complex)).calculate()   # above the size limit
     with pytest.raises(Exception):
         pqb.GlynnPermanentCalculator_wrapper(np.eye(3), 3).calculate()    # DFE id
-    with pytest.raises(Exception):
-        pqb.GlynnRepeatedInfPermanentCalculator(np.eye(3), [1, 1, 1], [1, 1, 1]).calculate()  # MPFR id
 
 
 def test_inf_request_is_served_by_the_double_double_mode(pqb, ref):

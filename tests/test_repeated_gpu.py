@@ -144,3 +144,28 @@ def test_every_repeated_kernel_instantiation(pqb, ref, photons):
         else:
             ref_double_err = relerr(ref.bbfg_repeated(U, inp, out, False), want)
             assert err < 1e-10 or err < 10 * ref_double_err, (photons, inp, out, got, want, ref_double_err)
+
+
+def test_double_double_repeated_mode(pqb, ref):
+    """pqb200_permanent_repeated_dd (a straight double-double walk of the reference's n-ary Gray code)
+    against the unmodified reference's long double repeated calculator; also serves lib 9 (GlynnRepInf)."""
+    from piquassoboost_b200.Boson_Sampling_Utilities import permanent_repeated_double_double
+    rng = np.random.default_rng(99)
+    for m, photons in [(4, 5), (5, 9), (6, 12), (8, 16), (7, 7), (5, 22)]:
+        U = haar_unitary(m, 60 + m)
+        inp = rng.multinomial(photons, [1 / m] * m).astype(np.int64)
+        out = rng.multinomial(photons, [1 / m] * m).astype(np.int64)
+        want = ref.bbfg_repeated(U, inp, out, True)
+        got, parts = permanent_repeated_double_double(U, inp, out)
+        assert relerr(got, want) < 2e-15, (m, photons, inp, out, got, want)
+        # the fast kernel agrees with the double-double truth as well
+        assert relerr(pqb.BBFGRepeatedPermanentCalculatorDouble(U, inp, out).calculate(), got) < 1e-10
+    U = haar_unitary(6, 5)
+    ones, = [np.array([1, 1, 1, 0, 1, 0])]
+    assert relerr(permanent_repeated_double_double(U, ones, ones[::-1].copy())[0],
+                  ref.bbfg_repeated(U, ones, ones[::-1].copy(), True)) < 2e-15         # all singles
+    assert permanent_repeated_double_double(U, np.zeros(6, int), np.zeros(6, int))[0] == 1.0
+    with pytest.raises(Exception):
+        permanent_repeated_double_double(U, [1, 0, 0, 0, 0, 0], [2, 0, 0, 0, 0, 0])
+    a, b = np.array([2, 0, 1, 0, 1, 0]), np.array([0, 1, 1, 1, 0, 1])
+    assert relerr(pqb.GlynnRepeatedInfPermanentCalculator(U, a, b).calculate(), ref.bbfg_repeated(U, a, b, True)) < 2e-15
