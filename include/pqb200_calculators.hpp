@@ -47,8 +47,13 @@ class BBFGPermanentCalculator {
 public:
     template <class Matrix>
     Complex16 calculate(Matrix& mtx, bool use_extended = false, bool use_inf = false) {
-        (void)use_extended;  // one numeric mode serves double and long double requests
-        if (use_inf) throw std::string("MPFR Not included");  // BBFGPermanentCalculator.cpp:100-107
+        (void)use_extended;  // one fast numeric mode serves double and long double requests
+        if (use_inf) {       // MPFR in the reference (BBFGPermanentCalculator.cpp:100-107): double-double here
+            double dd[4];
+            check(pqb200_permanent_dd(reinterpret_cast<const double*>(mtx.get_data()), mtx.rows, mtx.cols,
+                                      mtx.stride, default_ndev(), dd));
+            return Complex16(dd[0] + dd[1], dd[2] + dd[3]);
+        }
         double out[2];
         check(pqb200_permanent(reinterpret_cast<const double*>(mtx.get_data()), mtx.rows, mtx.cols,
                                mtx.stride, default_ndev(), out));
@@ -82,10 +87,15 @@ public:
     Complex16 calculate(Matrix& mtx, State& col_mult, State& row_mult, bool use_extended = false,
                         bool use_inf = false) {
         (void)use_extended;
-        if (use_inf) throw std::string("MPFR Not included");
         std::vector<int64_t> c(col_mult.size()), r(row_mult.size());
         for (size_t i = 0; i < c.size(); i++) c[i] = (int64_t)col_mult[i];
         for (size_t i = 0; i < r.size(); i++) r[i] = (int64_t)row_mult[i];
+        if (use_inf) {  // MPFR in the reference (BBFGPermanentCalculatorRepeated.cpp:117-124): double-double here
+            double dd[4];
+            check(pqb200_permanent_repeated_dd(reinterpret_cast<const double*>(mtx.get_data()), mtx.rows,
+                                               mtx.cols, mtx.stride, r.data(), c.data(), default_ndev(), dd));
+            return Complex16(dd[0] + dd[1], dd[2] + dd[3]);
+        }
         double out[2];
         check(pqb200_permanent_repeated(reinterpret_cast<const double*>(mtx.get_data()), mtx.rows,
                                         mtx.cols, mtx.stride, r.data(), c.data(), default_ndev(), out));

@@ -29,6 +29,10 @@ int main() {
         auto w = pqb200::GlynnPermanentCalculator().calculate(m);
         std::printf("repeated=(%.15g,%.15g) plain=(%.15g,%.15g)\n", v.real(), v.imag(), w.real(), w.imag());
         if (std::abs(v - std::complex<double>(-1, 0)) > 1e-14) return 2;
+        // use_inf requests (MPFR in the reference) are served by the double-double modes
+        auto vi = pqb200::BBFGPermanentCalculatorRepeated().calculate(m, in, out, false, true);
+        auto wi = pqb200::BBFGPermanentCalculator().calculate(m, false, true);
+        if (std::abs(vi - v) > 1e-15 || std::abs(wi - w) > 1e-15) return 5;
         // BatchednPermanentCalculator: two state pairs against the same interferometer
         State in2{{1, 1}}, out2{{1, 1}};
         pqb200::BatchednPermanentCalculator<Mat, State> batch(m);
