@@ -236,3 +236,13 @@ def test_block_diagonal_n42_full_size(pqb, ref):
     want = ref.bbfg(A, True) * ref.bbfg(B, True)
     got = pqb.GlynnPermanent(M).calculate()
     assert relerr(got, want) < 1e-10, (got, want)
+
+
+def test_n40_haar_submatrix_vs_committed_double_double(pqb):
+    """BASELINE config C3, second input class: the top-left 40x40 block of a Haar
+    unitary of size 80, against the committed double-double evaluation (tools/accuracy_subblock.py)."""
+    from scipy.stats import unitary_group
+    gold = _golden_dd()["40_sub80"]
+    want = complex(*[float.fromhex(x) for x in gold["dd_parts_hex"]][0::2])
+    A = np.ascontiguousarray(unitary_group.rvs(80, random_state=80)[:40, :40])
+    assert relerr(pqb.GlynnPermanent(A).calculate(), want) < 1e-11

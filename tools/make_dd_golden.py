@@ -9,6 +9,7 @@ Inputs (both produced by committed scripts):
     reference's long double BBFG calculator on the same matrices (96 s / 423 s / 1861 s on 8 cores).
 
 usage: python tools/make_dd_golden.py gpurun_out/accuracy.jsonl scratch/ref_big_32_34_36.json
+(the "40_sub80" case is appended from the output of tools/accuracy_subblock.py 40)
 """
 import json
 import os
