@@ -41,7 +41,11 @@ def main(acc_path, ref_path):
         out["cases"][n]["ref_long_double"] = [r["re_f"], r["im_f"]]
         out["cases"][n]["ref_long_double_seconds_8_cores"] = r["seconds"]
         out["cases"][n]["dd_rel_err_vs_ref"] = abs(d - v) / abs(v)
-    json.dump(out, open(os.path.join(ROOT, "tests", "golden", "plain_dd_reference.json"), "w"), indent=1)
+    path = os.path.join(ROOT, "tests", "golden", "plain_dd_reference.json")
+    if os.path.exists(path):  # keep cases made by other tools (e.g. "40_sub80" from tools/accuracy_subblock.py)
+        for key, case in json.load(open(path))["cases"].items():
+            out["cases"].setdefault(key, case)
+    json.dump(out, open(path, "w"), indent=1)
     print({n: c.get("dd_rel_err_vs_ref") for n, c in out["cases"].items()})
 
 
