@@ -15,10 +15,22 @@
  *     returns a message for the calling thread.  The C++ shims turn that into `throw std::string`
  *     (the reference's error convention, e.g. BBFGPermanentCalculatorRepeated.hpp:122-123);
  *   - there is NO CPU fallback: without a usable CUDA device every compute call fails;
- *   - calls are serialised internally (one mutex), so the library may be called from the TBB
- *     workers of samplingHelperFunctions.cpp:137 -- but the batched entry points are the intended
- *     replacement for that loop.
- *   - `ndev`: number of GPUs to shard one call over (0 = all initialised devices).
+ *   - the library is re-entrant: every call owns a WORK SLOT (stream + workspaces; two per device)
+ *     from its first enqueue to its last synchronise, calls on different GPUs -- and two calls on the
+ *     same GPU -- run concurrently, so it may be called from the TBB workers of
+ *     samplingHelperFunctions.cpp:137 (the batched entry points remain the intended replacement for
+ *     that loop).  The caller's current CUDA device is restored before every return.
+ *   - `ndev`: GPUs one call is sharded over.
+ *       0  automatic: as many devices as the call's work is worth (about one per millisecond of
+ *          estimated kernel time, at most pqb200_init's count) -- a 14x14 permanent runs on ONE GPU,
+ *          an n=40 permanent on all of them.  A one-device call runs on the calling thread's current
+ *          CUDA device (cudaSetDevice / torch.cuda.set_device; device 0 if never set) and moves to
+ *          another initialised GPU when that device's slots are busy;
+ *       1  the calling thread's current CUDA device;
+ *      >=2 devices 0 .. ndev-1.
+ *   - asynchronous entry points (pqb200_permanent_shard with d_out, pqb200_permanent_nccl_async) leave
+ *     work in flight on the caller's stream; the library orders every later use of the same slot
+ *     behind it (cudaStreamWaitEvent), so they may be mixed freely with the blocking calls.
  */
 #ifndef PQB200_H
 #define PQB200_H
@@ -84,10 +96,12 @@ int pqb200_permanent_nccl(const double* a, size_t rows, size_t cols, size_t stri
 int pqb200_permanent_nccl_async(const double* a, size_t rows, size_t cols, size_t stride,
                                 double* d_gathered, void* stream);
 
-/* perm(A) of a square matrix (2 <= n <= 45) with EVERY operation in double-double arithmetic
- * (~106 mantissa bits): the engine's counterpart of the reference's extended-precision request
+/* perm(A) with EVERY operation in double-double arithmetic (~106 mantissa bits): the engine's
+ * counterpart of the reference's extended-precision request
  *   BBFGPermanentCalculator::calculate(mtx, use_extended=true)  sampling/source/BBFGPermanentCalculator.cpp:109-116
- * (x87 long double there).  About 25x slower than pqb200_permanent; it exists to give ground truth at
+ * (x87 long double there).  Same shapes and edge semantics as pqb200_permanent (empty -> 1, rows >=
+ * cols+2 -> 0, one row -> product of its entries, rectangular input -> the reference's sum over the
+ * `cols` column sums).  About 25x slower than pqb200_permanent; it exists to give ground truth at
  * sizes the CPU reference cannot reach (n=40) and is sharded over `ndev` devices the same way.
  * out_dd = re.hi re.lo im.hi im.lo of the scaled permanent. */
 int pqb200_permanent_dd(const double* a, size_t rows, size_t cols, size_t stride, int ndev,
@@ -115,7 +129,16 @@ int pqb200_permanent_batch(const double* const* a, const size_t* rows, const siz
  *   GlynnPermanentCalculatorRepeated<M,P>::calculate(matrix&, input_state, output_state)
  *                                                sampling/source/GlynnPermanentCalculatorRepeated.hpp:49-74
  * Returns PQB200_ERR_MISMATCH when the photon numbers differ (the reference throws std::string,
- * BBFGPermanentCalculatorRepeated.hpp:119-124). */
+ * BBFGPermanentCalculatorRepeated.hpp:119-124).
+ * Evaluated in the reference's power form (column sums raised to their multiplicity, hpp:263-275):
+ * no photon-number cap; the limits are 45 distinct rows x 48 distinct columns on the two sides after
+ * the orientation choice, and multiplicities <= 254.
+ * Precision dispatch: the kernel also returns sum|term|; when the a-posteriori rounding bound
+ * eps*(photons+8)*sum|term|/|sum| exceeds 2e-8 the call is re-evaluated in double-double arithmetic
+ * (pqb200_permanent_repeated_dd) -- the engine's form of the reference's use_extended / use_inf
+ * dispatch (BBFGPermanentCalculatorRepeated.cpp:105-141).  pqb200_last_repeated_bound reports the
+ * bound of the calling thread's most recent repeated permanent and whether it was re-evaluated. */
+int pqb200_last_repeated_bound(double* bound, int* used_dd);
 int pqb200_permanent_repeated(const double* a, size_t rows, size_t cols, size_t stride,
                               const int64_t* row_mult, const int64_t* col_mult, int ndev,
                               double out[2]);
@@ -152,7 +175,8 @@ int pqb200_seed(uint64_t seed);
  * one into input mode insert_modes[s*nmax+k] (update_input_by_single_photon with its random choice
  * already resolved), computes the pmf layer and picks the output mode with the uniform draw
  * draws[s*nmax+k] exactly as sample_from_pmf does (samplingHelperFunctions.cpp:350-374).  One kernel
- * launch per device; one CTA per shot runs all of its photon steps.  nmax <= 40.
+ * thread-block cluster (1-8 CTAs) per shot runs all of its photon steps; the shots are cut into
+ * waves that alternate over the devices.  nmax <= 40.
  * samples_out: shots x m. */
 int pqb200_fill_r_samples(const double* u, size_t m, size_t stride, size_t shots, size_t nmax,
                           const int32_t* nphot, const uint8_t* insert_modes, const double* draws,

@@ -72,6 +72,7 @@ _SIGNATURES = {
         [c_double_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, c_int64_p, c_int64_p,
          ctypes.c_int, c_double_p],
     ),
+    "pqb200_last_repeated_bound": (ctypes.c_int, [c_double_p, ctypes.POINTER(ctypes.c_int)]),
     "pqb200_permanent_repeated_dd": (
         ctypes.c_int,
         [c_double_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, c_int64_p, c_int64_p,
@@ -177,6 +178,15 @@ def dptr(arr):
 
 def iptr(arr):
     return arr.ctypes.data_as(c_int64_p)
+
+
+def last_repeated_bound():
+    """(a-posteriori rounding bound, re-evaluated in double-double?) of this thread's most recent
+    repeated permanent (pqb200_last_repeated_bound)."""
+    b = ctypes.c_double(0.0)
+    d = ctypes.c_int(0)
+    check(load().pqb200_last_repeated_bound(ctypes.byref(b), ctypes.byref(d)))
+    return b.value, bool(d.value)
 
 
 def last_stats():

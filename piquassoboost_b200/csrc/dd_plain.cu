@@ -21,6 +21,7 @@ constexpr int kDDMaxN = 45;
 
 struct PlainDDParams {
     const double* a;  // device, rows x n interleaved complex (row-major, dense)
+    int rows;         // 2 <= rows <= n (rows < n: the caller padded the columns, see pqb200_permanent_dd)
     int n;
     int L;
     unsigned long long chunk_begin, chunk_end;
@@ -33,7 +34,7 @@ struct PlainDDParams {
 __device__ __forceinline__ void dd_acc_scaled(dd& acc, double x) { dd_add_d(acc, x); }
 
 __global__ void __launch_bounds__(kPlainThreads, 1) glynn_plain_dd_kernel(const PlainDDParams p) {
-    const int n = p.n;
+    const int n = p.n, rows = p.rows;
     const int L = p.L;
     const unsigned int nsteps = 1u << L;
     const unsigned long long nthreads = (unsigned long long)gridDim.x * kPlainThreads;
@@ -50,8 +51,8 @@ __global__ void __launch_bounds__(kPlainThreads, 1) glynn_plain_dd_kernel(const 
             ci[j].hi = __ldg(p.a + 2 * j + 1);
             ci[j].lo = 0.0;
         }
-        for (int i = 1; i < n; i++) {
-            const double d = ((gray0 >> (n - 1 - i)) & 1ull) ? -1.0 : 1.0;
+        for (int i = 1; i < rows; i++) {
+            const double d = ((gray0 >> (rows - 1 - i)) & 1ull) ? -1.0 : 1.0;
             const double* row = p.a + 2 * (size_t)i * n;
             for (int j = 0; j < n; j++) {
                 dd_add_d(cr[j], d * __ldg(row + 2 * j));
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(kPlainThreads, 1) glynn_plain_dd_kernel(const 
                 const int b = __ffs(s1) - 1;
                 const unsigned long long g = g0 + s1;
                 const double sg = (((g >> b) ^ (g >> (b + 1))) & 1ull) ? -2.0 : 2.0;
-                const double* row = p.a + 2 * (size_t)(n - 1 - b) * n;
+                const double* row = p.a + 2 * (size_t)(rows - 1 - b) * n;
                 for (int j = 0; j < n; j++) {
                     dd_add_d(cr[j], sg * __ldg(row + 2 * j));
                     dd_add_d(ci[j], sg * __ldg(row + 2 * j + 1));
@@ -95,11 +96,12 @@ __global__ void __launch_bounds__(kPlainThreads, 1) glynn_plain_dd_kernel(const 
     grid_reduce_cdd<kPlainThreads>(tot, p.partials, p.counter, p.out);
 }
 
-cudaError_t launch_plain_dd(const double* d_a, int n, int L, unsigned long long cb, unsigned long long ce,
+cudaError_t launch_plain_dd(const double* d_a, int rows, int n, int L, unsigned long long cb, unsigned long long ce,
                             int grid, double* partials, unsigned int* counter, double* out,
                             cudaStream_t stream) {
     PlainDDParams p;
     p.a = d_a;
+    p.rows = rows;
     p.n = n;
     p.L = L;
     p.chunk_begin = cb;

@@ -17,14 +17,16 @@
 
 namespace pqb200 {
 
-constexpr int kDDRepMaxN = 44;
-constexpr int kDDRepMaxD = 44;
+constexpr int kDDRepMaxN = kPowMaxC;       // distinct product-side columns (multiplicities are powers)
+constexpr int kDDRepMaxD = kPowMaxDigits;
 
 struct RepDDParams {
     const double* mat;    // device, R x N interleaved complex; row 0 = anchor, rows 1..D = digit rows
-    const double* binom;  // device, [D][kDDRepMaxN + 1]
-    int D, N;
-    unsigned char r[kDDRepMaxD];  // multiplicity of digit row d+1 (radix r[d] + 1)
+    const double* binom;  // device, [D][binom_stride][2]: C(r_d, k) as a double-double (hi, lo)
+    int binom_stride;
+    int D, N;             // N: distinct columns
+    unsigned char r[kDDRepMaxD];   // multiplicity of digit row d+1 (radix r[d] + 1)
+    unsigned char cm[kDDRepMaxN];  // multiplicity of column j: its column sum enters the product cm[j] times
     unsigned long long begin, end;  // this launch's range of the counter
     unsigned long long per_thread;
     double* partials;
@@ -80,25 +82,31 @@ __global__ void __launch_bounds__(kPlainThreads, 1) glynn_repeated_dd_kernel(con
         }
         cdd acc = cdd_zero();
         for (unsigned long long t = lo; t < hi; t++) {
-            // weight (exact: a product of binomials < 2^53) and sign of this term
-            double w = 1.0;
+            // weight (a product of binomials, each given as an exact double-double) and sign of this term
+            dd w;
+            w.hi = 1.0;
+            w.lo = 0.0;
             int ksum = 0;
             for (int d = 0; d < D; d++) {
-                w *= __ldg(p.binom + d * (kDDRepMaxN + 1) + k[d]);
+                dd b;
+                b.hi = __ldg(p.binom + 2 * (d * p.binom_stride + k[d]));
+                b.lo = __ldg(p.binom + 2 * (d * p.binom_stride + k[d]) + 1);
+                w = dd_mul_dd(w, b);
                 ksum += k[d];
             }
-            if (ksum & 1) w = -w;
+            if (ksum & 1) w = dd_neg(w);
+            // prod_j colsum_j^cm_j by repeated multiplication (BBFGPermanentCalculatorRepeated.hpp:263-275)
             cdd q;
             q.re = cr[0];
             q.im = ci[0];
-            for (int j = 1; j < N; j++) {
+            for (int j = 0; j < N; j++) {
                 cdd f;
                 f.re = cr[j];
                 f.im = ci[j];
-                q = cdd_mul(q, f);
+                for (int e = (j == 0 ? 1 : 0); e < (int)p.cm[j]; e++) q = cdd_mul(q, f);
             }
-            q.re = dd_mul_d(q.re, w);
-            q.im = dd_mul_d(q.im, w);
+            q.re = dd_mul_dd(q.re, w);
+            q.im = dd_mul_dd(q.im, w);
             cdd_add(acc, q);
             if (t + 1 < hi) {
                 // n_aryGrayCodeCounter::next: increment the counter, recompute the reflected digits; exactly
@@ -132,15 +140,17 @@ __global__ void __launch_bounds__(kPlainThreads, 1) glynn_repeated_dd_kernel(con
     grid_reduce_cdd<kPlainThreads>(tot, p.partials, p.counter, p.out);
 }
 
-cudaError_t launch_repeated_dd(const double* d_mat, const double* d_binom, int D, int N, const int* r,
-                               unsigned long long begin, unsigned long long end, int max_blocks,
+cudaError_t launch_repeated_dd(const double* d_mat, const double* d_binom, int binom_stride, int D, int N,
+                               const int* r, const int* cm, unsigned long long begin, unsigned long long end, int max_blocks,
                                double* partials, unsigned int* counter, double* out, cudaStream_t stream) {
     RepDDParams p;
     p.mat = d_mat;
     p.binom = d_binom;
     p.D = D;
     p.N = N;
+    p.binom_stride = binom_stride;
     for (int d = 0; d < kDDRepMaxD; d++) p.r[d] = (unsigned char)(d < D ? r[d] : 0);
+    for (int j = 0; j < kDDRepMaxN; j++) p.cm[j] = (unsigned char)(j < N ? cm[j] : 1);
     p.begin = begin;
     p.end = end;
     const unsigned long long total = end - begin;

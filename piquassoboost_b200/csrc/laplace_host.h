@@ -19,8 +19,18 @@ struct LapLaunch {
     const unsigned char* d_cur_in;
     double* d_pmf;
     unsigned long long* d_gray_terms;
+    const int* d_order;  // [shots] shot index handled by cluster i (NULL = identity)
+    int cluster;         // CTAs per shot: 1, 2, 4 or 8
     int mode;  // 0: whole shots (fill_r_sample), 1: one pmf layer
 };
+
+// CTAs per shot such that shots x cluster covers the device's CTA slots about `waves` times
+inline int lap_cluster_for(size_t shots, int sm_count) {
+    const size_t slots = (size_t)sm_count * 3;
+    int cs = 1;
+    while (cs < 8 && shots * (size_t)cs < 6 * slots) cs *= 2;
+    return cs;
+}
 
 cudaError_t lap_init_device(void);  // binomial table of the current device
 cudaError_t lap_launch(const LapLaunch& l, cudaStream_t stream);

@@ -37,9 +37,23 @@ cudaError_t lap_launch(const LapLaunch& l, cudaStream_t stream) {
     a.cur_in = l.d_cur_in;
     a.pmf_out = l.d_pmf;
     a.gray_terms = l.d_gray_terms;
+    a.order = l.d_order;
     a.mode = l.mode;
-    laplace_sampler_kernel<<<l.shots, kLapThreads, 0, stream>>>(a);
-    return cudaGetLastError();
+    const int cs = (l.cluster == 2 || l.cluster == 4 || l.cluster == 8) ? l.cluster : 1;
+    static_assert(kLapMaxCluster == 8, "cluster sizes");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)l.shots * (unsigned)cs, 1, 1);
+    cfg.blockDim = dim3(kLapThreads, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, laplace_sampler_kernel, a);
 }
 
 }  // namespace pqb200

@@ -15,9 +15,13 @@
 // ~14 N FP64 instructions per term instead of k * 6 N.
 //
 // GPU layout.
-//   * One CTA (128 threads) per shot, all photon steps in one launch: insertion order and the
-//     uniform draws of the shot are pre-resolved on the host from the reference's std::mt19937 stream
-//     (they do not depend on the pmf values), so there is no host round trip between steps.
+//   * One thread-block CLUSTER (1, 2, 4 or 8 CTAs of 128 threads) per shot, all photon steps in one
+//     launch: insertion order and the uniform draws of the shot are pre-resolved on the host from the
+//     reference's std::mt19937 stream (they do not depend on the pmf values), so there is no host round
+//     trip between steps.  The CTAs of a cluster split the chunks of every Gray sweep and combine their
+//     partial addends through distributed shared memory in a fixed order; the host picks the cluster
+//     size so that shots x cluster covers the GPU several times (a 125-shot shard of an 8-GPU run would
+//     otherwise occupy a quarter of the SMs) and hands out the shots in descending photon count.
 //   * Per step the CTA builds the job in shared memory (rows / radices from `sample`, physically
 //     repeated columns from `cur`, gather of the sub-matrix from U = adaptInterferometer), the
 //     low-digit step table and the two base vectors -- same low/high digit split of the reflected
@@ -29,6 +33,7 @@
 //     form the m amplitudes; thread 0 normalises and draws exactly as sample_from_pmf does.
 // The same kernel serves pqb200_pmf_layer (mode 1: `sample`/`cur` given, one step, pmf written out).
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -41,6 +46,7 @@ constexpr int kLapThreads = 128;
 constexpr int kLapMaxPhotons = 40;  // columns of a step (photons inserted so far)
 constexpr int kLapMaxLen = 512;     // low-digit steps per chunk
 constexpr int kLapBinomDim = 48;
+constexpr int kLapMaxCluster = 8;   // CTAs that share one shot (portable cluster size limit)
 
 static __constant__ double c_lap_binom[kLapBinomDim][kLapBinomDim];
 
@@ -50,6 +56,7 @@ struct LapArgs {
     int m;
     int shots;
     int nmax;                        // row length of ins / rnd
+    const int* order;                // [shots] shot handled by cluster i (descending cost), NULL = identity
     const int* nphot;                // [shots] photon steps of the shot                    (mode 0)
     const unsigned char* ins;        // [shots][nmax] input mode of the k-th inserted photon (mode 0)
     const double* rnd;               // [shots][nmax] uniform draw of step k                 (mode 0)
@@ -66,6 +73,7 @@ struct LapShared {
     double2 base[2][kLapMaxPhotons];
     RepStep table[kLapMaxLen];
     double2 red[kLapThreads / 32][kLapMaxPhotons];
+    double2 cred[kLapMaxCluster][kLapMaxPhotons];  // rank 0: the partial addends of every CTA of the cluster
     double2 addend[kLapMaxPhotons];
     double p[256];
     unsigned long long highW[kLapMaxPhotons];
@@ -92,7 +100,7 @@ __host__ __device__ __forceinline__ int lap_bucket(int N) {
 
 // One Gray sweep of the current step: fills sh.addend[0..N) (unscaled by 2^-(K-1)).
 template <int NC, int LP>
-__device__ __noinline__ void lap_sweep(LapShared& sh) {
+__device__ __noinline__ void lap_sweep(LapShared& sh, const unsigned int crank, const unsigned int csize) {
     constexpr int G = kLapThreads / LP;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = tid / LP, c0 = (tid % LP) * NC;
@@ -103,9 +111,10 @@ __device__ __noinline__ void lap_sweep(LapShared& sh) {
     double ar[NC], ai[NC];
 #pragma unroll
     for (int j = 0; j < NC; j++) ar[j] = ai[j] = 0.0;
-    const unsigned long long iters = (nchunks + G - 1) / G;
+    const unsigned long long per_it = (unsigned long long)G * csize;  // chunks the cluster takes per iteration
+    const unsigned long long iters = (nchunks + per_it - 1) / per_it;
     for (unsigned long long it = 0; it < iters; it++) {
-        const unsigned long long c = it * G + (unsigned long long)g;
+        const unsigned long long c = it * per_it + (unsigned long long)crank * G + (unsigned long long)g;
         const bool live = c < nchunks;
         const unsigned long long cc = live ? c : 0ull;
         // high digits (most significant first): reflected Gray values, parity, binomial weight and
@@ -212,11 +221,29 @@ __device__ __noinline__ void lap_sweep(LapShared& sh) {
         sh.addend[tid] = make_double2(re, im);
     }
     __syncthreads();
+    if (csize > 1) {
+        // cluster reduction through distributed shared memory: every CTA stores its partial addends
+        // into rank 0's `cred`, rank 0 folds them in rank order (deterministic)
+        namespace cg = cooperative_groups;
+        cg::cluster_group cluster = cg::this_cluster();
+        LapShared* sh0 = cluster.map_shared_rank(&sh, 0);
+        if (tid < sh.N) sh0->cred[crank][tid] = sh.addend[tid];
+        cluster.sync();
+        if (crank == 0 && tid < sh.N) {
+            double re = 0.0, im = 0.0;
+            for (unsigned int r = 0; r < csize; r++) {
+                re += sh.cred[r][tid].x;
+                im += sh.cred[r][tid].y;
+            }
+            sh.addend[tid] = make_double2(re, im);
+        }
+        __syncthreads();
+    }
 }
 
 // Build the step's job in shared memory from sh.sample / sh.cur (thread 0), then gather and tabulate
 // (all threads).  Returns with everything lap_sweep needs in place.
-__device__ __forceinline__ void lap_prepare(LapShared& sh, const LapArgs& a) {
+__device__ __forceinline__ void lap_prepare(LapShared& sh, const LapArgs& a, const unsigned int csize) {
     const int tid = threadIdx.x, m = a.m;
     if (tid == 0) {
         // rows: occupied output modes; the anchor takes one copy of the first minimum-multiplicity
@@ -251,11 +278,12 @@ __device__ __forceinline__ void lap_prepare(LapShared& sh, const LapArgs& a) {
         sh.R = R;
         sh.N = N;
         sh.K = K;
-        // low / high digit split: chunks of at most kLapMaxLen steps, >= 4 chunks per term owner
+        // low / high digit split: chunks of at most kLapMaxLen steps, >= 8 chunks per term owner of the
+        // cluster (the last round of chunks is partly idle: at most 1/8 of the sweep)
         double total = 1.0;
         for (int d = 0; d < R - 1; d++) total *= (double)sh.radix[d];
-        const int G = kLapThreads / lap_lanes(N);
-        double want = total / (4.0 * G);
+        const int G = kLapThreads / lap_lanes(N) * (int)csize;
+        double want = total / (8.0 * G);
         want = want < 1.0 ? 1.0 : want > (double)kLapMaxLen ? (double)kLapMaxLen : want;
         unsigned int len = 1;
         int q = 0;
@@ -330,8 +358,13 @@ __device__ __forceinline__ void lap_prepare(LapShared& sh, const LapArgs& a) {
 }
 
 __global__ void __launch_bounds__(kLapThreads, 3) laplace_sampler_kernel(const LapArgs a) {
+    namespace cg = cooperative_groups;
     __shared__ LapShared sh;
-    const int tid = threadIdx.x, m = a.m, s = blockIdx.x;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned int csize = cluster.num_blocks(), crank = cluster.block_rank();
+    const int tid = threadIdx.x, m = a.m;
+    const int slot = (int)(blockIdx.x / csize);
+    const int s = a.order ? a.order[slot] : slot;
     int steps;
     if (a.mode == 0) {
         for (int i = tid; i < m; i += kLapThreads) sh.sample[i] = sh.cur[i] = 0;
@@ -344,15 +377,17 @@ __global__ void __launch_bounds__(kLapThreads, 3) laplace_sampler_kernel(const L
         steps = 1;
     }
     __syncthreads();
+    // every CTA of the cluster keeps its own copy of the shot's state (sample, cur) and prepares each
+    // step redundantly; only the Gray sweep is split
     for (int k = 0; k < steps; k++) {
         if (a.mode == 0) {
             // update_input_by_single_photon (samplingHelperFunctions.cpp:377-406), order pre-resolved
             if (tid == 0) sh.cur[a.ins[(size_t)s * a.nmax + k]]++;
             __syncthreads();
         }
-        lap_prepare(sh, a);
+        lap_prepare(sh, a, csize);
         const int N = sh.N;
-        if (tid == 0 && sh.R > 0) atomicAdd(a.gray_terms, (unsigned long long)sh.len * sh.nchunks);
+        if (tid == 0 && crank == 0 && sh.R > 0) atomicAdd(a.gray_terms, (unsigned long long)sh.len * sh.nchunks);
         if (sh.R == 0) {
             // no photon placed yet: every sub-permanent is the empty permanent 1 (hpp:126-128)
             if (tid < N) sh.addend[tid] = make_double2(1.0, 0.0);
@@ -360,66 +395,75 @@ __global__ void __launch_bounds__(kLapThreads, 3) laplace_sampler_kernel(const L
         } else {
             switch (lap_bucket(N)) {
                 // one lane per term: NC = 2,4,..,10
-                case 1: lap_sweep<2, 1>(sh); break;
-                case 2: lap_sweep<4, 1>(sh); break;
-                case 3: lap_sweep<6, 1>(sh); break;
-                case 4: lap_sweep<8, 1>(sh); break;
-                case 5: lap_sweep<10, 1>(sh); break;
+                case 1: lap_sweep<2, 1>(sh, crank, csize); break;
+                case 2: lap_sweep<4, 1>(sh, crank, csize); break;
+                case 3: lap_sweep<6, 1>(sh, crank, csize); break;
+                case 4: lap_sweep<8, 1>(sh, crank, csize); break;
+                case 5: lap_sweep<10, 1>(sh, crank, csize); break;
                 // two lanes per term: N = 11..20 -> NC = 6..10
-                case 11: lap_sweep<6, 2>(sh); break;
-                case 12: lap_sweep<7, 2>(sh); break;
-                case 13: lap_sweep<8, 2>(sh); break;
-                case 14: lap_sweep<9, 2>(sh); break;
-                case 15: lap_sweep<10, 2>(sh); break;
+                case 11: lap_sweep<6, 2>(sh, crank, csize); break;
+                case 12: lap_sweep<7, 2>(sh, crank, csize); break;
+                case 13: lap_sweep<8, 2>(sh, crank, csize); break;
+                case 14: lap_sweep<9, 2>(sh, crank, csize); break;
+                case 15: lap_sweep<10, 2>(sh, crank, csize); break;
                 // four lanes per term: N = 21..40 -> NC = 6..10
-                case 21: lap_sweep<6, 4>(sh); break;
-                case 22: lap_sweep<7, 4>(sh); break;
-                case 23: lap_sweep<8, 4>(sh); break;
-                case 24: lap_sweep<9, 4>(sh); break;
-                default: lap_sweep<10, 4>(sh); break;
+                case 21: lap_sweep<6, 4>(sh, crank, csize); break;
+                case 22: lap_sweep<7, 4>(sh, crank, csize); break;
+                case 23: lap_sweep<8, 4>(sh, crank, csize); break;
+                case 24: lap_sweep<9, 4>(sh, crank, csize); break;
+                default: lap_sweep<10, 4>(sh, crank, csize); break;
             }
         }
-        // ---- amplitudes and probabilities of the m output modes (samplingHelperFunctions.cpp:308-339)
-        const double sc = sh.K > 0 ? ldexp(1.0, -(sh.K - 1)) : 1.0;
-        for (int mm = tid; mm < m; mm += kLapThreads) {
-            double re = 0.0, im = 0.0;
-            for (int j = 0; j < N; j++) {
-                if (!sh.first[j]) continue;
-                const int col = sh.pidx[j];
-                const double cw = (double)sh.cur[col] * sc;
-                const double wr = cw * sh.addend[j].x, wi = cw * sh.addend[j].y;
-                const double2 u = a.U[(size_t)mm * a.ustride + col];
-                re += wr * u.x - wi * u.y;
-                im += wr * u.y + wi * u.x;
-            }
-            sh.p[mm] = re * re + im * im;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            double tot = 0.0;
-            for (int i = 0; i < m; i++) tot += sh.p[i];
-            if (a.mode == 0) {
-                // sample_from_pmf (samplingHelperFunctions.cpp:350-374): first index whose cumulative
-                // normalised probability reaches the draw, 0 if none does
-                const double r = a.rnd[(size_t)s * a.nmax + k];
-                int chosen = 0;
-                double acc = 0.0;
-                for (int i = 0; i < m; i++) {
-                    acc += sh.p[i] / tot;
-                    if (acc >= r) { chosen = i; break; }
+        // ---- amplitudes and probabilities of the m output modes (samplingHelperFunctions.cpp:308-339):
+        //      rank 0 of the cluster holds the complete addends
+        if (crank == 0) {
+            const double sc = sh.K > 0 ? ldexp(1.0, -(sh.K - 1)) : 1.0;
+            for (int mm = tid; mm < m; mm += kLapThreads) {
+                double re = 0.0, im = 0.0;
+                for (int j = 0; j < N; j++) {
+                    if (!sh.first[j]) continue;
+                    const int col = sh.pidx[j];
+                    const double cw = (double)sh.cur[col] * sc;
+                    const double wr = cw * sh.addend[j].x, wi = cw * sh.addend[j].y;
+                    const double2 u = a.U[(size_t)mm * a.ustride + col];
+                    re += wr * u.x - wi * u.y;
+                    im += wr * u.y + wi * u.x;
                 }
-                sh.sample[chosen]++;
-            } else {
-                sh.p[255] = tot;  // m <= 255: slot 255 is free
+                sh.p[mm] = re * re + im * im;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double tot = 0.0;
+                for (int i = 0; i < m; i++) tot += sh.p[i];
+                if (a.mode == 0) {
+                    // sample_from_pmf (samplingHelperFunctions.cpp:350-374): first index whose cumulative
+                    // normalised probability reaches the draw, 0 if none does
+                    const double r = a.rnd[(size_t)s * a.nmax + k];
+                    int chosen = 0;
+                    double acc = 0.0;
+                    for (int i = 0; i < m; i++) {
+                        acc += sh.p[i] / tot;
+                        if (acc >= r) { chosen = i; break; }
+                    }
+                    for (unsigned int r2 = 0; r2 < csize; r2++) cluster.map_shared_rank(&sh, r2)->chosen = chosen;
+                } else {
+                    sh.p[255] = tot;  // m <= 255: slot 255 is free
+                }
             }
         }
-        __syncthreads();
+        if (csize > 1) cluster.sync(); else __syncthreads();
+        if (a.mode == 0) {
+            if (tid == 0) sh.sample[sh.chosen]++;
+            __syncthreads();
+        }
     }
-    if (a.mode == 0) {
-        for (int i = tid; i < m; i += kLapThreads) a.samples_out[(size_t)s * m + i] = (long long)sh.sample[i];
-    } else {
-        const double tot = sh.p[255];
-        for (int i = tid; i < m; i += kLapThreads) a.pmf_out[(size_t)s * m + i] = sh.p[i] / tot;
+    if (crank == 0) {
+        if (a.mode == 0) {
+            for (int i = tid; i < m; i += kLapThreads) a.samples_out[(size_t)s * m + i] = (long long)sh.sample[i];
+        } else {
+            const double tot = sh.p[255];
+            for (int i = tid; i < m; i += kLapThreads) a.pmf_out[(size_t)s * m + i] = sh.p[i] / tot;
+        }
     }
 }
 

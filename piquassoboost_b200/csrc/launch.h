@@ -23,29 +23,48 @@ struct PlainLaunchArgs {
 typedef cudaError_t (*plain_launch_fn)(const PlainLaunchArgs&);
 typedef int (*plain_occupancy_fn)(void);  // resident CTAs per SM on the current device (<=0: error)
 
-struct RepLaunchArgs {
-    const double* mat;  // host, interleaved complex, R x N (row 0 = anchor, columns physically repeated)
-    int R, N;
+// ---- power-form repeated kernel (glynn_reppow.cuh)
+constexpr int kPowMaxC = 48;        // distinct product-side columns
+constexpr int kPowMaxDigits = 44;   // Gray-side rows besides the anchor
+constexpr int kPowBufBytes = 32128; // matrix + step tables inside the kernel-parameter bank
+constexpr int kPowLenCap = 4096;
+constexpr int kPowTableSize = 64;
+
+#ifdef __CUDACC__
+#define PQB_HD __host__ __device__
+#else
+#define PQB_HD
+#endif
+PQB_HD constexpr int pow_row_stride(int c) { return c % 16 == 0 ? c + 1 : c; }
+// steps per chunk that fit the parameter bank next to an R x C matrix (10 bytes per step)
+inline int pow_len_max(int R, int C) {
+    const int v = (kPowBufBytes - 16 * R * pow_row_stride(C) - 64) / 10;
+    return v > kPowLenCap ? kPowLenCap : v;
+}
+
+struct PowLaunchArgs {
+    const double* mat;  // host, interleaved complex, R x C (row 0 = anchor), normalised, NOT doubled
+    int R, C;
+    const unsigned char* cmult;  // [C] column multiplicities (>= 1), in the kernel's column order
     int q;
     unsigned int len;
     unsigned long long chunk_begin, chunk_end;
-    int grid;
+    int sm_count;                      // the launcher sizes the grid: resident CTAs per SM x sm_count
     const unsigned char* radix;        // [R-1]
     const unsigned long long* weight;  // [R-1]
     const void* table;                 // HOST, RepStepHost[len] (copied into the kernel parameters)
-    const void* base;                  // device, double2[2][N]
-    const double* binom;               // device, [R-1][kRepBinomStride]
+    const void* base;                  // device, double2[2][C]
+    const double* binom;               // device, [R-1][binom_stride]
+    int binom_stride;
     int low_parity[2];
-    double phase[4];                   // dd complex correction factor of the normalisation
-    double* partials;
+    double phase[4];
+    double* partials;                  // [grid][8]
     unsigned int* counter;
-    double* out;
+    double* out;                       // 5 doubles
     cudaStream_t stream;
 };
+typedef cudaError_t (*pow_launch_fn)(const PowLaunchArgs&);
 
-typedef cudaError_t (*rep_launch_fn)(const RepLaunchArgs&);
-
-constexpr int kRepBinomStride = 45;  // kRepMaxN + 1
 constexpr int kPlainTableSize = 64;
 constexpr int kPlainThreads = 256;  // CTA size of glynn_plain_kernel
 

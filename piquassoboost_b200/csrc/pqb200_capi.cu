@@ -38,51 +38,81 @@ PQB_DECL_FILL(31)
 PQB_DECL_FILL(36)
 PQB_DECL_FILL(40)
 PQB_DECL_FILL(43)
-#define PQB_DECL_REP_FILL(lo) extern "C" void pqb200_rep_fill_##lo(rep_launch_fn*);
-PQB_DECL_REP_FILL(2)
-PQB_DECL_REP_FILL(17)
-PQB_DECL_REP_FILL(25)
-PQB_DECL_REP_FILL(31)
-PQB_DECL_REP_FILL(36)
-PQB_DECL_REP_FILL(40)
-PQB_DECL_REP_FILL(43)
+// registered by the glynn_reppow_inst.cu units (one per range of distinct column counts C)
+#define PQB_DECL_POW_FILL(lo) extern "C" void pqb200_pow_fill_##lo(pow_launch_fn*);
+PQB_DECL_POW_FILL(1)
+PQB_DECL_POW_FILL(9)
+PQB_DECL_POW_FILL(17)
+PQB_DECL_POW_FILL(25)
+PQB_DECL_POW_FILL(33)
+PQB_DECL_POW_FILL(41)
+#define PQB_POW_FILL_CALLS                                                                      \
+    pqb200_pow_fill_1(g_pow_launch); pqb200_pow_fill_9(g_pow_launch); pqb200_pow_fill_17(g_pow_launch); \
+    pqb200_pow_fill_25(g_pow_launch); pqb200_pow_fill_33(g_pow_launch); pqb200_pow_fill_41(g_pow_launch);
 
 namespace pqb200 {
-cudaError_t launch_repeated_dd(const double* d_mat, const double* d_binom, int D, int N, const int* r,
-                               unsigned long long begin, unsigned long long end, int max_blocks,
-                               double* partials, unsigned int* counter, double* out, cudaStream_t stream);
-cudaError_t launch_plain_dd(const double* d_a, int n, int L, unsigned long long cb, unsigned long long ce,
+cudaError_t launch_repeated_dd(const double* d_mat, const double* d_binom, int binom_stride, int D, int N,
+                               const int* r, const int* cm, unsigned long long begin, unsigned long long end,
+                               int max_blocks, double* partials, unsigned int* counter, double* out,
+                               cudaStream_t stream);
+cudaError_t launch_plain_dd(const double* d_a, int rows, int n, int L, unsigned long long cb, unsigned long long ce,
                             int grid, double* partials, unsigned int* counter, double* out,
                             cudaStream_t stream);
 }
 
 namespace {
 
-// keep in sync with rep_len_max() in glynn_repeated.cuh (steps per chunk that fit the parameter space)
-inline int rep_len_max_host(int n) {
-    const int v = (32764 - 16 * n * plain_row_stride(n) - 704) / 10;
-    return v > 4096 ? 4096 : v;
-}
-
 constexpr int kMaxPlainN = 45;
 constexpr int kMaxChunkLog = 12;  // full re-seed of the running column sums every 2^12 steps
 constexpr int kSubChunkLog = 8;   // ... and re-derivation from the per-thread anchor every 2^8 steps
 constexpr int kMaxGridBlocks = 4096;
-constexpr int kMaxRepN = 44;
+constexpr int kMaxDevices = 64;
+constexpr int kSlotsPerDevice = 2;
+// FP64 instructions one GPU gets through in about a millisecond: a call with `ndev == 0` (automatic) is
+// spread over ceil(work / kWorkPerDevice) devices, so that small calls touch ONE GPU
+constexpr double kWorkPerDevice = 2.0e10;
 
+struct LapDeviceBuffers {
+    void* nphot = nullptr;   size_t nphot_cap = 0;
+    void* ins = nullptr;     size_t ins_cap = 0;
+    void* rnd = nullptr;     size_t rnd_cap = 0;
+    void* samples = nullptr; size_t samples_cap = 0;
+    void* sin = nullptr;     size_t sin_cap = 0;
+    void* cin = nullptr;     size_t cin_cap = 0;
+    void* pmf = nullptr;     size_t pmf_cap = 0;
+    void* order = nullptr;   size_t order_cap = 0;
+    void* h_stage = nullptr; size_t h_stage_cap = 0;  // pinned host staging of the sampler's waves
+    unsigned long long* terms = nullptr;  // [0] Gray terms swept, [1] work-queue head
+    bool ready = false;
+};
+
+// One WORK SLOT of one device: a stream plus every workspace a call needs.  A call owns the slots it
+// runs on (slot mutex held from the first enqueue to the last synchronise); calls on different
+// devices -- and up to kSlotsPerDevice calls on the same device -- run concurrently.
 struct DeviceCtx {
     int dev = -1;
+    int slot = 0;
     int sm_count = 0;
+    std::mutex mu;
     cudaStream_t stream = nullptr;
     double* partials = nullptr;  // kMaxGridBlocks x 4
     unsigned int* counter = nullptr;
-    double* d_out = nullptr;  // 4 doubles
-    double* h_out = nullptr;  // pinned, 4 doubles
+    double* d_out = nullptr;  // 8 doubles
+    double* h_out = nullptr;  // pinned, 8 doubles
     cudaEvent_t e0 = nullptr, e1 = nullptr;
+    // Recorded behind work that an asynchronous entry point (pqb200_permanent_shard with d_out,
+    // pqb200_permanent_nccl_async) left in flight on a CALLER's stream: every later use of the slot's
+    // workspaces is ordered behind it with cudaStreamWaitEvent.
+    cudaEvent_t busy = nullptr;
+    bool busy_pending = false;
+    bool dirty = false;  // a call failed half-way: drain the stream and reset the counter before reuse
     int occ[kPlainTableSize];
-    // repeated-row kernel tables (device): step table, base vectors, binomials, low parities
-    void* rep_base = nullptr;
-    double* rep_binom = nullptr;
+    // repeated-row kernel tables (device): base vectors, binomials
+    void* rep_base = nullptr;    size_t rep_base_cap = 0;
+    void* rep_binom = nullptr;   size_t rep_binom_cap = 0;
+    // double-double entry points: matrix and binomial table
+    void* dd_a = nullptr;        size_t dd_a_cap = 0;
+    void* dd_b = nullptr;        size_t dd_b_cap = 0;
     // batch path: growable device buffers (matrix data, job descriptors, results, pmf scratch)
     void* b_u = nullptr;      size_t b_u_cap = 0;
     void* b_jobs = nullptr;   size_t b_jobs_cap = 0;
@@ -90,14 +120,18 @@ struct DeviceCtx {
     void* b_weight = nullptr; size_t b_weight_cap = 0;
     void* b_pmf = nullptr;    size_t b_pmf_cap = 0;
     bool batch_ready = false;
+    LapDeviceBuffers lap;
 };
 
+// g_mu guards library-wide state only (device discovery and slot creation, the default device
+// count, the NCCL communicator, the reference's global random generator); it is never held while a
+// kernel runs.
 std::mutex g_mu;
-std::vector<DeviceCtx> g_devs;
+DeviceCtx g_slots[kMaxDevices][kSlotsPerDevice];
 bool g_tables_ready = false;
 plain_launch_fn g_plain_launch[kPlainTableSize];
 plain_occupancy_fn g_plain_occ[kPlainTableSize];
-rep_launch_fn g_rep_launch[kPlainTableSize];
+pow_launch_fn g_pow_launch[kPowTableSize];
 
 thread_local std::string g_err;
 thread_local pqb200_stats g_stats = {0.0, 0.0, 0, 0};
@@ -136,23 +170,29 @@ void fill_tables() {
     pqb200_plain_fill_36(g_plain_launch, g_plain_occ);
     pqb200_plain_fill_40(g_plain_launch, g_plain_occ);
     pqb200_plain_fill_43(g_plain_launch, g_plain_occ);
-    memset(g_rep_launch, 0, sizeof(g_rep_launch));
-    pqb200_rep_fill_2(g_rep_launch);
-    pqb200_rep_fill_17(g_rep_launch);
-    pqb200_rep_fill_25(g_rep_launch);
-    pqb200_rep_fill_31(g_rep_launch);
-    pqb200_rep_fill_36(g_rep_launch);
-    pqb200_rep_fill_40(g_rep_launch);
-    pqb200_rep_fill_43(g_rep_launch);
+    memset(g_pow_launch, 0, sizeof(g_pow_launch));
+    PQB_POW_FILL_CALLS
     g_tables_ready = true;
 }
 
 int g_visible = -1;      // CUDA devices visible to this process
-int g_default_ndev = 0;  // devices one call is sharded over when the caller passes ndev == 0
+int g_default_ndev = 0;  // devices one call may be sharded over when the caller passes ndev == 0
 
-// caller holds g_mu.  Creates the per-device context (stream, workspaces) on first use only, so
-// that a one-process-per-GPU job touches nothing but its own device.
-int get_device(int dev, DeviceCtx** out) {
+int grow(void** p, size_t* cap, size_t need) {
+    if (need <= *cap) return PQB200_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    const size_t want = std::max(need, (size_t)1 << 16) * 3 / 2;
+    CUDA_TRY(cudaMalloc(p, want));
+    *cap = want;
+    return PQB200_OK;
+}
+
+
+// caller holds g_mu.  Creates the slot (stream, workspaces) on first use only, so that a
+// one-process-per-GPU job touches nothing but its own device.
+int get_device(int dev, int slot, DeviceCtx** out) {
     fill_tables();
     if (g_visible < 0) {
         int visible = 0;
@@ -161,11 +201,11 @@ int get_device(int dev, DeviceCtx** out) {
             return fail(PQB200_ERR_CUDA,
                         std::string("no usable CUDA device (libpqb200 has no CPU fallback): ") +
                             (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
-        g_visible = visible;
-        g_devs.resize((size_t)visible);
+        g_visible = std::min(visible, kMaxDevices);
     }
     if (dev < 0 || dev >= g_visible) return fail(PQB200_ERR_ARG, "device index out of range");
-    DeviceCtx& c = g_devs[(size_t)dev];
+    if (slot < 0 || slot >= kSlotsPerDevice) return fail(PQB200_ERR_ARG, "slot index out of range");
+    DeviceCtx& c = g_slots[dev][slot];
     if (c.dev < 0) {
         CUDA_TRY(cudaSetDevice(dev));
         cudaDeviceProp prop;
@@ -174,16 +214,16 @@ int get_device(int dev, DeviceCtx** out) {
             return fail(PQB200_ERR_CUDA, std::string("device ") + prop.name +
                                              " is not sm_100 class; this library is built for B200 only");
         c.sm_count = prop.multiProcessorCount;
+        c.slot = slot;
         CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaMalloc(&c.partials, sizeof(double) * 4 * kMaxGridBlocks));
+        CUDA_TRY(cudaMalloc(&c.partials, sizeof(double) * 8 * kMaxGridBlocks));
         CUDA_TRY(cudaMalloc(&c.counter, sizeof(unsigned int)));
         CUDA_TRY(cudaMemset(c.counter, 0, sizeof(unsigned int)));
-        CUDA_TRY(cudaMalloc(&c.d_out, sizeof(double) * 4));
-        CUDA_TRY(cudaMallocHost(&c.h_out, sizeof(double) * 4));
+        CUDA_TRY(cudaMalloc(&c.d_out, sizeof(double) * 8));
+        CUDA_TRY(cudaMallocHost(&c.h_out, sizeof(double) * 8));
         CUDA_TRY(cudaEventCreate(&c.e0));
         CUDA_TRY(cudaEventCreate(&c.e1));
-        CUDA_TRY(cudaMalloc(&c.rep_base, 16 * 2 * (size_t)kMaxRepN));
-        CUDA_TRY(cudaMalloc(&c.rep_binom, sizeof(double) * kMaxRepN * kRepBinomStride));
+        CUDA_TRY(cudaEventCreateWithFlags(&c.busy, cudaEventDisableTiming));
         for (int i = 0; i < kPlainTableSize; i++) c.occ[i] = 0;
         c.dev = dev;
     }
@@ -193,26 +233,153 @@ int get_device(int dev, DeviceCtx** out) {
 
 // caller holds g_mu
 int init_locked(int ndev) {
-    int rc = get_device(0, nullptr);
+    int rc = get_device(0, 0, nullptr);
     if (rc) return rc;
     if (ndev <= 0 || ndev > g_visible) ndev = g_visible;
     g_default_ndev = ndev;
     return PQB200_OK;
 }
 
-// resolves the `ndev` argument of a compute call and makes sure those devices have contexts
-int ensure_devices(int ndev, int* used) {
-    if (g_default_ndev == 0) {
-        int rc = init_locked(0);
+// The slots one call runs on, locked; released (and the caller's current CUDA device restored) when
+// the lease goes out of scope.  A call that returns early with an error leaves its slots marked
+// dirty: the next owner drains them before use.
+struct Lease {
+    std::vector<DeviceCtx*> slots;
+    int saved_dev = -1;
+    bool ok = false;
+    Lease() = default;
+    Lease(const Lease&) = delete;
+    Lease& operator=(const Lease&) = delete;
+    ~Lease() { release(); }
+    void release() {
+        for (DeviceCtx* c : slots) {
+            if (!ok) c->dirty = true;
+            c->mu.unlock();
+        }
+        slots.clear();
+        if (saved_dev >= 0) cudaSetDevice(saved_dev);
+        saved_dev = -1;
+    }
+    int size() const { return (int)slots.size(); }
+    DeviceCtx& operator[](int i) const { return *slots[(size_t)i]; }
+    int done(int rc) {
+        ok = (rc == PQB200_OK);
+        return rc;
+    }
+};
+
+// after the slot mutex has been taken
+int slot_prepare(DeviceCtx& c) {
+    if (c.dirty || c.busy_pending) CUDA_TRY(cudaSetDevice(c.dev));
+    if (c.dirty) {
+        cudaStreamSynchronize(c.stream);
+        cudaGetLastError();
+        CUDA_TRY(cudaMemsetAsync(c.counter, 0, sizeof(unsigned int), c.stream));
+        c.dirty = false;
+    }
+    if (c.busy_pending) {
+        if (cudaEventQuery(c.busy) == cudaSuccess) c.busy_pending = false;
+        else CUDA_TRY(cudaStreamWaitEvent(c.stream, c.busy, 0));
+    }
+    return PQB200_OK;
+}
+
+// Resolve the `ndev` argument of a compute call and lock the slots it runs on.
+//   ndev >= 2 : devices 0..ndev-1 (slot 0 of each, taken in ascending order);
+//   ndev == 1 : the calling thread's current CUDA device (cudaSetDevice / torch.cuda.set_device; 0 if
+//               never set), whichever of its slots is free;
+//   ndev == 0 : automatic -- ceil(work / kWorkPerDevice) devices, at most pqb200_init's count; a call
+//               that needs ONE device prefers the current device and moves to another initialised
+//               device when both of its slots are busy (concurrent callers spread over the GPUs).
+// `work` = estimated FP64 instructions of the call.
+int acquire(int ndev, double work, Lease& ls) {
+    int used, pref = 0;
+    bool roam = false;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (g_default_ndev == 0) {
+            int rc = init_locked(0);
+            if (rc) return rc;
+        }
+        if (ndev <= 0) {
+            const double want = std::ceil(work / kWorkPerDevice);
+            used = want >= (double)g_default_ndev ? g_default_ndev : std::max(1, (int)want);
+            roam = true;
+        } else {
+            used = std::min(ndev, g_visible);
+        }
+        cudaGetDevice(&ls.saved_dev);
+        if (used == 1) {
+            pref = ls.saved_dev;
+            if (pref < 0 || pref >= (roam ? g_default_ndev : g_visible)) pref = 0;
+            for (int s = 0; s < kSlotsPerDevice; s++) {
+                int rc = get_device(pref, s, nullptr);
+                if (rc) return rc;
+            }
+        } else {
+            for (int d = 0; d < used; d++) {
+                int rc = get_device(d, 0, nullptr);
+                if (rc) return rc;
+            }
+        }
+    }
+    if (used == 1) {
+        DeviceCtx* got = nullptr;
+        for (int s = 0; s < kSlotsPerDevice && !got; s++)
+            if (g_slots[pref][s].mu.try_lock()) got = &g_slots[pref][s];
+        if (!got && roam) {
+            for (int k = 1; k < g_default_ndev && !got; k++) {
+                const int d = (pref + k) % g_default_ndev;
+                for (int s = 0; s < kSlotsPerDevice && !got; s++) {
+                    DeviceCtx& c = g_slots[d][s];
+                    if (c.dev < 0) {  // not created yet: create it (first use of that GPU by this process)
+                        std::lock_guard<std::mutex> lk(g_mu);
+                        if (get_device(d, s, nullptr)) continue;
+                    }
+                    if (c.mu.try_lock()) got = &c;
+                }
+            }
+        }
+        if (!got) {
+            g_slots[pref][0].mu.lock();
+            got = &g_slots[pref][0];
+        }
+        ls.slots.push_back(got);
+    } else {
+        for (int d = 0; d < used; d++) {
+            g_slots[d][0].mu.lock();
+            ls.slots.push_back(&g_slots[d][0]);
+        }
+    }
+    for (DeviceCtx* c : ls.slots) {
+        int rc = slot_prepare(*c);
         if (rc) return rc;
     }
-    if (ndev <= 0) ndev = g_default_ndev;
-    if (ndev > g_visible) ndev = g_visible;
-    for (int d = 0; d < ndev; d++) {
-        int rc = get_device(d, nullptr);
+    return PQB200_OK;
+}
+
+// lock one given slot (the one-process-per-GPU entry points name their device)
+int acquire_device(int device, Lease& ls) {
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        cudaGetDevice(&ls.saved_dev);
+        int rc = get_device(device, 0, nullptr);
         if (rc) return rc;
     }
-    *used = ndev;
+    g_slots[device][0].mu.lock();
+    ls.slots.push_back(&g_slots[device][0]);
+    return slot_prepare(*ls.slots[0]);
+}
+
+// Order a launch on a CALLER's stream behind whatever an earlier asynchronous call left in flight
+// on this slot's workspaces.
+int order_behind_async(DeviceCtx& c, cudaStream_t st) {
+    if (c.busy_pending && st != c.stream) CUDA_TRY(cudaStreamWaitEvent(st, c.busy, 0));
+    return PQB200_OK;
+}
+int mark_async(DeviceCtx& c, cudaStream_t st) {
+    CUDA_TRY(cudaEventRecord(c.busy, st));
+    c.busy_pending = true;
     return PQB200_OK;
 }
 
@@ -267,11 +434,13 @@ int plain_occupancy(DeviceCtx& c, int N) {
     return c.occ[N];
 }
 
-// Launch the chunk range [cb, ce) of the plain kernel on device c (async on `stream`), result to `out`.
+// Launch the chunk range [cb, ce) of the plain kernel on slot c (async on `stream`), result to `out`.
 int launch_plain_range(DeviceCtx& c, const double* a, size_t rows, size_t cols, size_t stride,
                        const PlainPlan& pl, unsigned long long cb, unsigned long long ce,
                        double* out, cudaStream_t stream) {
     CUDA_TRY(cudaSetDevice(c.dev));
+    int rc = order_behind_async(c, stream);
+    if (rc) return rc;
     if (ce <= cb) {
         CUDA_TRY(cudaMemsetAsync(out, 0, 4 * sizeof(double), stream));
         return PQB200_OK;
@@ -300,8 +469,9 @@ int launch_plain_range(DeviceCtx& c, const double* a, size_t rows, size_t cols, 
 int check_plain_args(const double* a, size_t rows, size_t cols, size_t stride) {
     if (!a) return fail(PQB200_ERR_ARG, "matrix pointer is null");
     if (stride < cols) return fail(PQB200_ERR_ARG, "stride is smaller than the number of columns");
+    if (rows >= cols + 2) return PQB200_OK;  // the reference returns 0 for these whatever the size
     if (std::max(rows, cols) > (size_t)kMaxPlainN ||
-        (rows >= 2 && rows <= cols + 1 && plain_kernel_cols((int)rows, (int)cols) > kMaxPlainN))
+        (rows >= 2 && plain_kernel_cols((int)rows, (int)cols) > kMaxPlainN))
         return fail(PQB200_ERR_ARG, "matrix dimension exceeds 45 (kernel-parameter resident matrix limit of this build)");
     return PQB200_OK;
 }
@@ -350,15 +520,29 @@ void combine_partials(const double* parts, size_t count, size_t rows, double out
     out[1] = ldexp(tot.im.hi, e) + ldexp(tot.im.lo, e);
 }
 
+// FP64 instructions of one plain permanent (5.5N - 6.5 per Gray step)
+double plain_work(size_t rows, size_t cols) {
+    if (rows < 2 || rows >= cols + 2) return 0.0;
+    return ldexp(1.0, (int)rows - 1) * 5.5 * (double)plain_kernel_cols((int)rows, (int)cols);
+}
+
+// FP64 instructions of S photon steps with at most `photons` photons each (upper bound: all
+// occupations distinct): used only to choose the device count of an automatic call
+double laplace_work(double S, double photons) {
+    return S * ldexp(14.0 * photons, (int)std::min(photons, 60.0) - 1);
+}
+
+const RepLimits kRepLimits = {kPowMaxDigits, kPowMaxC, 254, kPowBufBytes, 32, kMaxPlainN};
+
 }  // namespace
 
 extern "C" {
 
-static void lap_release_all();
+static void lap_release(DeviceCtx& c);
 static void nccl_release_locked();
 
 const char* pqb200_last_error(void) { return g_err.c_str(); }
-const char* pqb200_version(void) { return "pqb200 0.1 (sm_100a)"; }
+const char* pqb200_version(void) { return "pqb200 0.2 (sm_100a)"; }
 
 int pqb200_init(int ndev) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -367,30 +551,47 @@ int pqb200_init(int ndev) {
 
 void pqb200_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
-    for (auto& c : g_devs) {
-        if (c.dev < 0) continue;
-        cudaSetDevice(c.dev);
-        cudaStreamSynchronize(c.stream);
-        cudaFree(c.partials);
-        cudaFree(c.counter);
-        cudaFree(c.d_out);
-        cudaFree(c.rep_base);
-        cudaFree(c.rep_binom);
-        cudaFree(c.b_u);
-        cudaFree(c.b_jobs);
-        cudaFree(c.b_out);
-        cudaFree(c.b_weight);
-        cudaFree(c.b_pmf);
-        cudaFreeHost(c.h_out);
-        cudaEventDestroy(c.e0);
-        cudaEventDestroy(c.e1);
-        cudaStreamDestroy(c.stream);
-    }
+    int saved = -1;
+    cudaGetDevice(&saved);
     nccl_release_locked();
-    lap_release_all();
-    g_devs.clear();
+    for (int d = 0; d < kMaxDevices; d++)
+        for (int sl = 0; sl < kSlotsPerDevice; sl++) {
+            DeviceCtx& c = g_slots[d][sl];
+            if (c.dev < 0) continue;
+            std::lock_guard<std::mutex> sk(c.mu);
+            cudaSetDevice(c.dev);
+            cudaStreamSynchronize(c.stream);
+            cudaFree(c.partials);
+            cudaFree(c.counter);
+            cudaFree(c.d_out);
+            cudaFree(c.rep_base);
+            cudaFree(c.rep_binom);
+            cudaFree(c.dd_a);
+            cudaFree(c.dd_b);
+            cudaFree(c.b_u);
+            cudaFree(c.b_jobs);
+            cudaFree(c.b_out);
+            cudaFree(c.b_weight);
+            cudaFree(c.b_pmf);
+            lap_release(c);
+            cudaFreeHost(c.h_out);
+            cudaEventDestroy(c.e0);
+            cudaEventDestroy(c.e1);
+            cudaEventDestroy(c.busy);
+            cudaStreamDestroy(c.stream);
+            c.partials = nullptr; c.counter = nullptr; c.d_out = nullptr; c.h_out = nullptr;
+            c.rep_base = c.rep_binom = c.dd_a = c.dd_b = nullptr;
+            c.rep_base_cap = c.rep_binom_cap = c.dd_a_cap = c.dd_b_cap = 0;
+            c.b_u = c.b_jobs = c.b_out = c.b_weight = c.b_pmf = nullptr;
+            c.b_u_cap = c.b_jobs_cap = c.b_out_cap = c.b_weight_cap = c.b_pmf_cap = 0;
+            c.batch_ready = false;
+            c.busy_pending = c.dirty = false;
+            c.stream = nullptr;
+            c.dev = -1;
+        }
     g_visible = -1;
     g_default_ndev = 0;
+    if (saved >= 0) cudaSetDevice(saved);
 }
 
 int pqb200_device_count(void) {
@@ -407,18 +608,19 @@ int pqb200_last_stats(pqb200_stats* out) {
     return PQB200_OK;
 }
 
-// perm of a rows x cols matrix (2 <= rows <= cols+1) over `used` devices; caller holds g_mu
-static int plain_multi_device(const double* a, size_t rows, size_t cols, size_t stride, int used,
+// perm of a rows x cols matrix (2 <= rows <= cols+1) over the leased devices
+static int plain_multi_device(Lease& ls, const double* a, size_t rows, size_t cols, size_t stride,
                               size_t scale_rows, double out[2]) {
     int rc;
-    const int max_threads = g_devs[0].sm_count * kPlainThreads;
+    int used = ls.size();
+    const int max_threads = ls[0].sm_count * kPlainThreads;
     PlainPlan pl = plan_plain((int)rows, (int)cols, max_threads, (unsigned long long)used);
     if ((unsigned long long)used > pl.nchunks) used = (int)pl.nchunks;
     std::vector<double> parts(4 * (size_t)used);
-    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
-    CUDA_TRY(cudaEventRecord(g_devs[0].e0, g_devs[0].stream));
+    CUDA_TRY(cudaSetDevice(ls[0].dev));
+    CUDA_TRY(cudaEventRecord(ls[0].e0, ls[0].stream));
     for (int d = 0; d < used; d++) {
-        DeviceCtx& c = g_devs[d];
+        DeviceCtx& c = ls[d];
         const unsigned long long cb = pl.nchunks * (unsigned long long)d / (unsigned long long)used;
         const unsigned long long ce = pl.nchunks * (unsigned long long)(d + 1) / (unsigned long long)used;
         rc = launch_plain_range(c, a, rows, cols, stride, pl, cb, ce, c.d_out, c.stream);
@@ -427,14 +629,14 @@ static int plain_multi_device(const double* a, size_t rows, size_t cols, size_t 
         if (d == 0) CUDA_TRY(cudaEventRecord(c.e1, c.stream));
     }
     for (int d = 0; d < used; d++) {
-        DeviceCtx& c = g_devs[d];
+        DeviceCtx& c = ls[d];
         CUDA_TRY(cudaSetDevice(c.dev));
         CUDA_TRY(cudaStreamSynchronize(c.stream));
         memcpy(&parts[4 * (size_t)d], c.h_out, 4 * sizeof(double));
     }
     float ms = 0.f;
-    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
-    CUDA_TRY(cudaEventElapsedTime(&ms, g_devs[0].e0, g_devs[0].e1));
+    CUDA_TRY(cudaSetDevice(ls[0].dev));
+    CUDA_TRY(cudaEventElapsedTime(&ms, ls[0].e0, ls[0].e1));
     g_stats.kernel_ms += ms;
     g_stats.gray_steps += ldexp(1.0, (int)rows - 1);
     g_stats.launches += (uint64_t)used;
@@ -450,61 +652,73 @@ int pqb200_permanent(const double* a, size_t rows, size_t cols, size_t stride, i
         int rc = check_plain_args(a, rows, cols, stride);
         if (rc) return rc;
     }
-    std::lock_guard<std::mutex> lk(g_mu);
-    int used = 0;
+    Lease ls;
     // the library must be usable (CUDA present) even for the trivial cases: no silent CPU path
-    int rc = ensure_devices(ndev, &used);
+    int rc = acquire(ndev, plain_work(rows, cols), ls);
     if (rc) return rc;
-    g_stats = {0.0, 0.0, 0, used};
-    if (plain_edge_case(a, rows, cols, stride, out)) return PQB200_OK;
-    return plain_multi_device(a, rows, cols, stride, used, rows, out);
+    g_stats = {0.0, 0.0, 0, ls.size()};
+    if (plain_edge_case(a, rows, cols, stride, out)) return ls.done(PQB200_OK);
+    return ls.done(plain_multi_device(ls, a, rows, cols, stride, rows, out));
 }
 
 int pqb200_permanent_dd(const double* a, size_t rows, size_t cols, size_t stride, int ndev,
                         double out_dd[4]) {
     if (!out_dd) return fail(PQB200_ERR_ARG, "output pointer is null");
-    int rc = check_plain_args(a, rows, cols, stride);
+    if (rows != 0 && cols != 0) {
+        int rc = check_plain_args(a, rows, cols, stride);
+        if (rc) return rc;
+    }
+    Lease ls;
+    int rc = acquire(ndev, 40.0 * plain_work(rows, cols), ls);
     if (rc) return rc;
-    if (rows != cols || rows < 2)
-        return fail(PQB200_ERR_ARG, "the double-double evaluation takes a square matrix with n >= 2");
-    std::lock_guard<std::mutex> lk(g_mu);
-    int used = 0;
-    rc = ensure_devices(ndev, &used);
-    if (rc) return rc;
-    const int n = (int)rows;
-    const int L = std::min(n - 1, kMaxChunkLog);
-    const unsigned long long nchunks = 1ull << (n - 1 - L);
+    int used = ls.size();
+    g_stats = {0.0, 0.0, 0, used};
+    {   // the reference's trivial branches (BBFGPermanentCalculator.hpp:90-95) come before everything else
+        double e[2];
+        if (plain_edge_case(a, rows, cols, stride, e)) {
+            out_dd[0] = e[0];
+            out_dd[1] = 0.0;
+            out_dd[2] = e[1];
+            out_dd[3] = 0.0;
+            return ls.done(PQB200_OK);
+        }
+    }
+    // rows != cols: the reference's sum runs over the `cols` column sums; as in the fast kernel the
+    // missing columns are the constant e_0 (column sum == 1 for every delta vector)
+    const int R = (int)rows, n = plain_kernel_cols((int)rows, (int)cols);
+    const int L = std::min(R - 1, kMaxChunkLog);
+    const unsigned long long nchunks = 1ull << (R - 1 - L);
     if ((unsigned long long)used > nchunks) used = (int)nchunks;
-    std::vector<double> dense(2 * (size_t)n * n);
-    for (int i = 0; i < n; i++) memcpy(&dense[2 * (size_t)i * n], a + 2 * i * stride, 16 * (size_t)n);
-    std::vector<double*> d_a((size_t)used, nullptr);
+    std::vector<double> dense(2 * (size_t)R * n, 0.0);
+    for (int i = 0; i < R; i++) memcpy(&dense[2 * (size_t)i * n], a + 2 * i * stride, 16 * cols);
+    for (int j = (int)cols; j < n; j++) dense[2 * (size_t)j] = 1.0;
     std::vector<double> parts(4 * (size_t)used);
-    g_stats = {0.0, ldexp(1.0, n - 1), (uint64_t)used, used};
-    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
-    CUDA_TRY(cudaEventRecord(g_devs[0].e0, g_devs[0].stream));
+    g_stats = {0.0, ldexp(1.0, R - 1), (uint64_t)used, used};
+    CUDA_TRY(cudaSetDevice(ls[0].dev));
+    CUDA_TRY(cudaEventRecord(ls[0].e0, ls[0].stream));
     for (int d = 0; d < used; d++) {
-        DeviceCtx& c = g_devs[d];
+        DeviceCtx& c = ls[d];
         CUDA_TRY(cudaSetDevice(c.dev));
-        CUDA_TRY(cudaMalloc(&d_a[d], 16 * (size_t)n * n));
-        CUDA_TRY(cudaMemcpyAsync(d_a[d], dense.data(), 16 * (size_t)n * n, cudaMemcpyHostToDevice, c.stream));
+        rc = grow(&c.dd_a, &c.dd_a_cap, 16 * (size_t)R * n);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c.dd_a, dense.data(), 16 * (size_t)R * n, cudaMemcpyHostToDevice, c.stream));
         const unsigned long long cb = nchunks * (unsigned long long)d / (unsigned long long)used;
         const unsigned long long ce = nchunks * (unsigned long long)(d + 1) / (unsigned long long)used;
         const unsigned long long want = (ce - cb + kPlainThreads - 1) / kPlainThreads;
         const int grid = (int)std::min<unsigned long long>(want, (unsigned long long)c.sm_count);
-        CUDA_TRY(launch_plain_dd(d_a[d], n, L, cb, ce, grid, c.partials, c.counter, c.d_out, c.stream));
+        CUDA_TRY(launch_plain_dd((const double*)c.dd_a, R, n, L, cb, ce, grid, c.partials, c.counter, c.d_out, c.stream));
         CUDA_TRY(cudaMemcpyAsync(c.h_out, c.d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
         if (d == 0) CUDA_TRY(cudaEventRecord(c.e1, c.stream));
     }
     for (int d = 0; d < used; d++) {
-        DeviceCtx& c = g_devs[d];
+        DeviceCtx& c = ls[d];
         CUDA_TRY(cudaSetDevice(c.dev));
-        CUDA_TRY(cudaStreamSynchronize(c.stream));
+        CUDA_TRY(cudaStreamSynchronize(c.stream));  // `dense` is a host temporary
         memcpy(&parts[4 * (size_t)d], c.h_out, 4 * sizeof(double));
-        CUDA_TRY(cudaFree(d_a[d]));
     }
     float ms = 0.f;
-    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
-    CUDA_TRY(cudaEventElapsedTime(&ms, g_devs[0].e0, g_devs[0].e1));
+    CUDA_TRY(cudaSetDevice(ls[0].dev));
+    CUDA_TRY(cudaEventElapsedTime(&ms, ls[0].e0, ls[0].e1));
     g_stats.kernel_ms = ms;
     cdd tot = cdd_zero();
     for (int d = 0; d < used; d++) {
@@ -515,71 +729,60 @@ int pqb200_permanent_dd(const double* a, size_t rows, size_t cols, size_t stride
         x.im.lo = parts[4 * d + 3];
         cdd_add(tot, x);
     }
-    const int e = -(n - 1);  // exact power-of-two scaling of both parts
+    const int e = -(R - 1);  // exact power-of-two scaling of both parts
     out_dd[0] = ldexp(tot.re.hi, e);
     out_dd[1] = ldexp(tot.re.lo, e);
     out_dd[2] = ldexp(tot.im.hi, e);
     out_dd[3] = ldexp(tot.im.lo, e);
-    return PQB200_OK;
+    return ls.done(PQB200_OK);
 }
 
-int pqb200_permanent_repeated_dd(const double* a, size_t rows, size_t cols, size_t stride,
-                                 const int64_t* row_mult, const int64_t* col_mult, int ndev,
-                                 double out_dd[4]) {
-    if (!out_dd) return fail(PQB200_ERR_ARG, "output pointer is null");
-    if (!row_mult || !col_mult) return fail(PQB200_ERR_ARG, "multiplicity pointer is null");
-    if (rows != 0 && cols != 0) {
-        if (!a) return fail(PQB200_ERR_ARG, "matrix pointer is null");
-        if (stride < cols) return fail(PQB200_ERR_ARG, "stride is smaller than the number of columns");
-    }
-    std::lock_guard<std::mutex> lk(g_mu);
-    int used = 0;
-    int rc = ensure_devices(ndev, &used);
-    if (rc) return rc;
-    RepPrepared pr;
-    std::string err;
-    rc = rep_prepare(a, rows, cols, stride, row_mult, col_mult, kMaxRepN, pr, err);
-    if (rc) return fail(rc, err);
-    out_dd[1] = out_dd[3] = 0.0;
-    if (pr.trivial) {
-        out_dd[0] = pr.value[0];
-        out_dd[2] = pr.value[1];
-        return PQB200_OK;
-    }
-    const int D = pr.R - 1, N = pr.N;
-    double total_d = 1.0;
-    unsigned long long total = 1;
-    for (int d = 0; d < D; d++) {
-        total_d *= (double)(pr.r[d] + 1);
-        total *= (unsigned long long)(pr.r[d] + 1);
-    }
+static double rep_total_steps(const RepPrepared& pr) {
+    double t = 1.0;
+    for (int m : pr.r) t *= (double)(m + 1);
+    return t;
+}
+
+// the double-double walk of a prepared repeated permanent over the leased devices
+static int repeated_dd_prepared(Lease& ls, const RepPrepared& pr, double out_dd[4]) {
+    int used = ls.size();
+    const int D = pr.R - 1, C = pr.C;
+    const double total_d = rep_total_steps(pr);
     if (total_d > 1.8e19) return fail(PQB200_ERR_ARG, "Gray space exceeds 2^64 steps");
-    std::vector<double> binom((size_t)std::max(D, 1) * kRepBinomStride, 0.0);
+    unsigned long long total = 1;
+    int maxr = 1;
+    for (int d = 0; d < D; d++) {
+        total *= (unsigned long long)(pr.r[d] + 1);
+        maxr = std::max(maxr, pr.r[d]);
+    }
+    const int bstride = maxr + 1;
+    std::vector<double> binom((size_t)std::max(D, 1) * bstride * 2, 0.0);
     for (int d = 0; d < D; d++)
-        for (int k = 0; k <= pr.r[d]; k++) binom[(size_t)d * kRepBinomStride + k] = binom_d(pr.r[d], k);
+        for (int k = 0; k <= pr.r[d]; k++)
+            binom_dd(pr.r[d], k, binom[2 * ((size_t)d * bstride + k)], binom[2 * ((size_t)d * bstride + k) + 1]);
     if ((unsigned long long)used > total) used = (int)total;
-    std::vector<double*> d_mat((size_t)used, nullptr), d_bin((size_t)used, nullptr);
-    std::vector<double> parts(4 * (size_t)used);
-    g_stats = {0.0, total_d, (uint64_t)used, used};
-    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
-    CUDA_TRY(cudaEventRecord(g_devs[0].e0, g_devs[0].stream));
+    g_stats.gray_steps += total_d;
+    g_stats.launches += (uint64_t)used;
+    CUDA_TRY(cudaSetDevice(ls[0].dev));
+    CUDA_TRY(cudaEventRecord(ls[0].e0, ls[0].stream));
     for (int d = 0; d < used; d++) {
-        DeviceCtx& c = g_devs[d];
+        DeviceCtx& c = ls[d];
         CUDA_TRY(cudaSetDevice(c.dev));
-        CUDA_TRY(cudaMalloc(&d_mat[d], sizeof(double) * pr.mat.size()));
-        CUDA_TRY(cudaMalloc(&d_bin[d], sizeof(double) * binom.size()));
-        CUDA_TRY(cudaMemcpyAsync(d_mat[d], pr.mat.data(), sizeof(double) * pr.mat.size(), cudaMemcpyHostToDevice, c.stream));
-        CUDA_TRY(cudaMemcpyAsync(d_bin[d], binom.data(), sizeof(double) * binom.size(), cudaMemcpyHostToDevice, c.stream));
+        int rc = grow(&c.dd_a, &c.dd_a_cap, sizeof(double) * pr.mat.size());
+        if (rc) return rc;
+        if ((rc = grow(&c.dd_b, &c.dd_b_cap, sizeof(double) * binom.size()))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c.dd_a, pr.mat.data(), sizeof(double) * pr.mat.size(), cudaMemcpyHostToDevice, c.stream));
+        CUDA_TRY(cudaMemcpyAsync(c.dd_b, binom.data(), sizeof(double) * binom.size(), cudaMemcpyHostToDevice, c.stream));
         const unsigned long long b = (unsigned long long)((__uint128_t)total * (unsigned)d / (unsigned)used);
         const unsigned long long e = (unsigned long long)((__uint128_t)total * (unsigned)(d + 1) / (unsigned)used);
-        CUDA_TRY(launch_repeated_dd(d_mat[d], d_bin[d], D, N, pr.r.data(), b, e, c.sm_count, c.partials,
-                                    c.counter, c.d_out, c.stream));
+        CUDA_TRY(launch_repeated_dd((const double*)c.dd_a, (const double*)c.dd_b, bstride, D, C, pr.r.data(),
+                                    pr.cm.data(), b, e, c.sm_count, c.partials, c.counter, c.d_out, c.stream));
         CUDA_TRY(cudaMemcpyAsync(c.h_out, c.d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
         if (d == 0) CUDA_TRY(cudaEventRecord(c.e1, c.stream));
     }
     cdd tot = cdd_zero();
     for (int d = 0; d < used; d++) {
-        DeviceCtx& c = g_devs[d];
+        DeviceCtx& c = ls[d];
         CUDA_TRY(cudaSetDevice(c.dev));
         CUDA_TRY(cudaStreamSynchronize(c.stream));
         cdd x;
@@ -588,13 +791,11 @@ int pqb200_permanent_repeated_dd(const double* a, size_t rows, size_t cols, size
         x.im.hi = c.h_out[2];
         x.im.lo = c.h_out[3];
         cdd_add(tot, x);
-        CUDA_TRY(cudaFree(d_mat[d]));
-        CUDA_TRY(cudaFree(d_bin[d]));
     }
     float ms = 0.f;
-    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
-    CUDA_TRY(cudaEventElapsedTime(&ms, g_devs[0].e0, g_devs[0].e1));
-    g_stats.kernel_ms = ms;
+    CUDA_TRY(cudaSetDevice(ls[0].dev));
+    CUDA_TRY(cudaEventElapsedTime(&ms, ls[0].e0, ls[0].e1));
+    g_stats.kernel_ms += ms;
     const int e = -(pr.photons - 1);
     out_dd[0] = ldexp(tot.re.hi, e);
     out_dd[1] = ldexp(tot.re.lo, e);
@@ -603,50 +804,105 @@ int pqb200_permanent_repeated_dd(const double* a, size_t rows, size_t cols, size
     return PQB200_OK;
 }
 
-// one repeated-row permanent over `used` devices; caller holds g_mu
-static int repeated_locked(const double* a, size_t rows, size_t cols, size_t stride,
-                           const int64_t* row_mult, const int64_t* col_mult, int used, double out[2]) {
+static int check_repeated_args(const double* a, size_t rows, size_t cols, size_t stride,
+                               const int64_t* row_mult, const int64_t* col_mult) {
+    if ((rows && !row_mult) || (cols && !col_mult)) return fail(PQB200_ERR_ARG, "multiplicity pointer is null");
+    if (rows && cols && !a) return fail(PQB200_ERR_ARG, "matrix pointer is null");
+    if (rows && cols && stride < cols) return fail(PQB200_ERR_ARG, "stride is smaller than the number of columns");
+    return PQB200_OK;
+}
+
+int pqb200_permanent_repeated_dd(const double* a, size_t rows, size_t cols, size_t stride,
+                                 const int64_t* row_mult, const int64_t* col_mult, int ndev,
+                                 double out_dd[4]) {
+    if (!out_dd) return fail(PQB200_ERR_ARG, "output pointer is null");
+    int rc = check_repeated_args(a, rows, cols, stride, row_mult, col_mult);
+    if (rc) return rc;
     RepPrepared pr;
     std::string err;
-    int rc = rep_prepare(a, rows, cols, stride, row_mult, col_mult, kMaxRepN, pr, err);
+    RepLimits lim = kRepLimits;
+    lim.buf_bytes = 1 << 30;  // the double-double walk reads the matrix from global memory
+    lim.max_plain_n = 1 << 20;
+    rc = rep_prepare(a, rows, cols, stride, row_mult, col_mult, lim, pr, err);
     if (rc) return fail(rc, err);
+    Lease ls;
+    rc = acquire(ndev, pr.trivial ? 0.0 : rep_total_steps(pr) * 200.0 * pr.photons, ls);
+    if (rc) return rc;
+    g_stats = {0.0, 0.0, 0, ls.size()};
+    out_dd[1] = out_dd[3] = 0.0;
+    if (pr.trivial) {
+        out_dd[0] = pr.value[0];
+        out_dd[2] = pr.value[1];
+        return ls.done(PQB200_OK);
+    }
+    return ls.done(repeated_dd_prepared(ls, pr, out_dd));
+}
+
+// A-posteriori rounding-error bound of the fast repeated kernel: eps * (photons + 8) * sum|term| /
+// |sum|.  Every term is a product of `photons` FP64 factors, each carrying a few roundings of its
+// column sum; the bound treats them as adding up linearly (worst case), so the true error is well
+// below it (tests/test_repeated_gpu.py records both).  Above kRepeatedDDThreshold the call is
+// re-evaluated in double-double arithmetic -- what the reference does up front by size / request
+// (BBFGPermanentCalculatorRepeated.cpp:105-141 use_extended / use_inf) is decided here by measurement.
+constexpr double kRepeatedDDThreshold = 2.0e-8;
+thread_local double g_last_bound = 0.0;
+thread_local int g_last_dd = 0;
+
+// one repeated-row permanent over the leased devices
+static int repeated_locked(Lease& ls, const double* a, size_t rows, size_t cols, size_t stride,
+                           const int64_t* row_mult, const int64_t* col_mult, double out[2]) {
+    int used = ls.size();
+    RepPrepared pr;
+    std::string err;
+    int rc = rep_prepare(a, rows, cols, stride, row_mult, col_mult, kRepLimits, pr, err);
+    if (rc) return fail(rc, err);
+    g_last_bound = 0.0;
+    g_last_dd = 0;
     if (pr.trivial) {
         out[0] = pr.value[0];
         out[1] = pr.value[1];
         return PQB200_OK;
     }
-    if (pr.all_single)  // every digit is binary: this is a plain permanent of the expanded matrix
-        return plain_multi_device(pr.mat.data(), (size_t)pr.R, (size_t)pr.N, (size_t)pr.N, used,
+    if (pr.plain_route)  // every digit is binary, no column repeats: a plain permanent
+        return plain_multi_device(ls, pr.mat.data(), (size_t)pr.R, (size_t)pr.C, (size_t)pr.C,
                                   (size_t)pr.photons, out);
+    const RepPrepared raw = pr;  // the double-double fallback takes the matrix as given
     rep_normalise(pr);
     RepPlan pl;
-    rep_plan(pr, g_devs[0].sm_count * kPlainThreads, (unsigned long long)used,
-             (unsigned int)rep_len_max_host(pr.N), kRepBinomStride, pl);
+    int maxr = 1;
+    for (int m : pr.r) maxr = std::max(maxr, m);
+    const int bstride = maxr + 1;
+    rep_plan(pr, ls[0].sm_count * kPlainThreads * 2, (unsigned long long)used,
+             (unsigned int)pow_len_max(pr.R, pr.C), bstride, pl);
     if ((unsigned long long)used > pl.nchunks) used = (int)pl.nchunks;
-    std::vector<double> parts(4 * (size_t)used);
+    std::vector<double> parts(5 * (size_t)used);
+    std::vector<unsigned char> cm(pr.cm.begin(), pr.cm.end());
     static_assert(sizeof(RepStepHost) == 16, "step table layout");
-    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
-    CUDA_TRY(cudaEventRecord(g_devs[0].e0, g_devs[0].stream));
+    CUDA_TRY(cudaSetDevice(ls[0].dev));
+    CUDA_TRY(cudaEventRecord(ls[0].e0, ls[0].stream));
     for (int d = 0; d < used; d++) {
-        DeviceCtx& c = g_devs[d];
+        DeviceCtx& c = ls[d];
         CUDA_TRY(cudaSetDevice(c.dev));
-        CUDA_TRY(cudaMemcpyAsync(c.rep_base, pl.base.data(), 16 * 2 * (size_t)pr.N, cudaMemcpyHostToDevice, c.stream));
+        if ((rc = grow(&c.rep_base, &c.rep_base_cap, 16 * 2 * (size_t)pr.C))) return rc;
+        if ((rc = grow(&c.rep_binom, &c.rep_binom_cap, sizeof(double) * pl.binom.size()))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c.rep_base, pl.base.data(), 16 * 2 * (size_t)pr.C, cudaMemcpyHostToDevice, c.stream));
         CUDA_TRY(cudaMemcpyAsync(c.rep_binom, pl.binom.data(), sizeof(double) * pl.binom.size(), cudaMemcpyHostToDevice, c.stream));
-        RepLaunchArgs x;
+        PowLaunchArgs x;
         x.mat = pr.mat.data();
         x.R = pr.R;
-        x.N = pr.N;
+        x.C = pr.C;
+        x.cmult = cm.data();
         x.q = pl.q;
         x.len = pl.len;
         x.chunk_begin = pl.nchunks * (unsigned long long)d / (unsigned long long)used;
         x.chunk_end = pl.nchunks * (unsigned long long)(d + 1) / (unsigned long long)used;
-        const unsigned long long want = (x.chunk_end - x.chunk_begin + kPlainThreads - 1) / kPlainThreads;
-        x.grid = (int)std::min<unsigned long long>(want, (unsigned long long)std::min(kMaxGridBlocks, c.sm_count));
+        x.sm_count = c.sm_count;
         x.radix = pl.radix;
         x.weight = pl.weight;
         x.table = pl.table.data();
         x.base = c.rep_base;
-        x.binom = c.rep_binom;
+        x.binom = (const double*)c.rep_binom;
+        x.binom_stride = bstride;
         x.low_parity[0] = pl.low_parity[0];
         x.low_parity[1] = pl.low_parity[1];
         for (int k = 0; k < 4; k++) x.phase[k] = pr.phase[k];
@@ -654,24 +910,57 @@ static int repeated_locked(const double* a, size_t rows, size_t cols, size_t str
         x.counter = c.counter;
         x.out = c.d_out;
         x.stream = c.stream;
-        CUDA_TRY(g_rep_launch[pr.N](x));
-        CUDA_TRY(cudaMemcpyAsync(c.h_out, c.d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        CUDA_TRY(g_pow_launch[pr.C](x));
+        CUDA_TRY(cudaMemcpyAsync(c.h_out, c.d_out, 5 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
         if (d == 0) CUDA_TRY(cudaEventRecord(c.e1, c.stream));
     }
+    double abs_sum = 0.0;
+    std::vector<double> p4(4 * (size_t)used);
     for (int d = 0; d < used; d++) {
-        DeviceCtx& c = g_devs[d];
+        DeviceCtx& c = ls[d];
         CUDA_TRY(cudaSetDevice(c.dev));
         CUDA_TRY(cudaStreamSynchronize(c.stream));  // also keeps pl / pr alive until the copies are done
-        memcpy(&parts[4 * (size_t)d], c.h_out, 4 * sizeof(double));
+        memcpy(&p4[4 * (size_t)d], c.h_out, 4 * sizeof(double));
+        abs_sum += c.h_out[4];
     }
     float ms = 0.f;
-    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
-    CUDA_TRY(cudaEventElapsedTime(&ms, g_devs[0].e0, g_devs[0].e1));
+    CUDA_TRY(cudaSetDevice(ls[0].dev));
+    CUDA_TRY(cudaEventElapsedTime(&ms, ls[0].e0, ls[0].e1));
     g_stats.kernel_ms += ms;
     g_stats.gray_steps += (double)pl.nchunks * (double)pl.len;
     g_stats.launches += (uint64_t)used;
     g_stats.ndev = used;
-    combine_partials(parts.data(), (size_t)used, (size_t)pr.photons, out);
+    // unscaled sum and its conditioning
+    cdd tot = cdd_zero();
+    for (int d = 0; d < used; d++) {
+        cdd x;
+        x.re.hi = p4[4 * d + 0];
+        x.re.lo = p4[4 * d + 1];
+        x.im.hi = p4[4 * d + 2];
+        x.im.lo = p4[4 * d + 3];
+        cdd_add(tot, x);
+    }
+    const double mag = hypot(tot.re.hi, tot.im.hi);
+    const double bound = mag > 0.0 ? 1.1102230246251565e-16 * (pr.photons + 8) * abs_sum / mag
+                                   : (abs_sum > 0.0 ? 1.0 : 0.0);
+    g_last_bound = bound;
+    static const bool no_dd = getenv("PQB200_NO_DD_FALLBACK") != nullptr;  // measurement aid
+    if (bound > kRepeatedDDThreshold && !no_dd) {
+        double dd4[4];
+        rc = repeated_dd_prepared(ls, raw, dd4);
+        if (rc) return rc;
+        g_last_dd = 1;
+        out[0] = dd4[0] + dd4[1];
+        out[1] = dd4[2] + dd4[3];
+        return PQB200_OK;
+    }
+    combine_partials(p4.data(), (size_t)used, (size_t)pr.photons, out);
+    return PQB200_OK;
+}
+
+int pqb200_last_repeated_bound(double* bound, int* used_dd) {
+    if (bound) *bound = g_last_bound;
+    if (used_dd) *used_dd = g_last_dd;
     return PQB200_OK;
 }
 
@@ -685,22 +974,24 @@ int pqb200_permanent_shard(const double* a, size_t rows, size_t cols, size_t str
     if (rc) return rc;
     if (rows < 2 || rows >= cols + 2)
         return fail(PQB200_ERR_ARG, "sharded evaluation needs 2 <= rows <= cols+1 (edge cases are not sharded)");
-    std::lock_guard<std::mutex> lk(g_mu);
-    DeviceCtx* cp = nullptr;
-    rc = get_device(device, &cp);
+    Lease ls;
+    rc = acquire_device(device, ls);
     if (rc) return rc;
-    DeviceCtx& c = *cp;
+    DeviceCtx& c = ls[0];
     PlainPlan pl = plan_plain((int)rows, (int)cols, c.sm_count * kPlainThreads, shard_count);
     const unsigned long long cb = (unsigned long long)((__uint128_t)pl.nchunks * shard_index / shard_count);
     const unsigned long long ce = (unsigned long long)((__uint128_t)pl.nchunks * (shard_index + 1) / shard_count);
-    cudaStream_t st = stream ? (cudaStream_t)stream : c.stream;
+    // NULL means the CALLER's legacy default stream when the result stays on the device (d_out): that is
+    // the stream a following collective or copy of the caller is ordered against.  With a host result
+    // the call synchronises itself and the library's own stream serves.
+    cudaStream_t st = stream ? (cudaStream_t)stream : (d_out ? cudaStreamLegacy : c.stream);
     double* dst = d_out ? d_out : c.d_out;
     CUDA_TRY(cudaSetDevice(c.dev));
     CUDA_TRY(cudaEventRecord(c.e0, st));
     rc = launch_plain_range(c, a, rows, cols, stride, pl, cb, ce, dst, st);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(c.e1, st));
-    g_stats = {0.0, ldexp(1.0, (int)rows - 1 - pl.L) > 0 ? (double)(ce - cb) * ldexp(1.0, pl.L) : 0.0, 1, 1};
+    g_stats = {0.0, (double)(ce - cb) * ldexp(1.0, pl.L), 1, 1};
     if (out_dd) {
         CUDA_TRY(cudaMemcpyAsync(c.h_out, dst, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
@@ -708,25 +999,18 @@ int pqb200_permanent_shard(const double* a, size_t rows, size_t cols, size_t str
         float ms = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&ms, c.e0, c.e1));
         g_stats.kernel_ms = ms;
+    } else if (st != c.stream) {
+        // work is left in flight on the caller's stream: later users of this slot's reduction
+        // workspace are ordered behind it
+        if ((rc = mark_async(c, st))) return rc;
     }
-    return PQB200_OK;
+    return ls.done(PQB200_OK);
 }
 
 int pqb200_permanent_combine(const double* partials_dd, size_t count, size_t rows, double out[2]) {
     if (!partials_dd || !out) return fail(PQB200_ERR_ARG, "null pointer");
     if (rows == 0) return fail(PQB200_ERR_ARG, "rows must be >= 1");
     combine_partials(partials_dd, count, rows, out);
-    return PQB200_OK;
-}
-
-static int grow(void** p, size_t* cap, size_t need) {
-    if (need <= *cap) return PQB200_OK;
-    if (*p) cudaFree(*p);
-    *p = nullptr;
-    *cap = 0;
-    const size_t want = std::max(need, (size_t)1 << 16) * 3 / 2;
-    CUDA_TRY(cudaMalloc(p, want));
-    *cap = want;
     return PQB200_OK;
 }
 
@@ -753,13 +1037,14 @@ static void single_row_value(const double* u, size_t ustride, const BatchJobHost
     out[1] = im;
 }
 
-// Runs the kernel jobs of `items` (all referring to matrix data already resident in c.b_u) on device
+// Runs the kernel jobs of `items` (all referring to matrix data already resident in c.b_u) on slot
 // c and leaves their results in c.b_out[out_slot]; trivial kinds must have been pre-filled by the
 // caller in `prefill` (count x complex), which is uploaded first.  Async on c.stream.
 static int run_batch_on_device(DeviceCtx& c, const std::vector<BatchItem>& items,
                                const std::vector<double>& prefill, size_t nslots) {
     CUDA_TRY(cudaSetDevice(c.dev));
     if (!c.batch_ready) {
+        std::lock_guard<std::mutex> lk(g_sym_mu);  // the binomial table is a per-device __constant__ symbol
         CUDA_TRY(batch_init_device());
         c.batch_ready = true;
     }
@@ -795,12 +1080,13 @@ static int run_batch_on_device(DeviceCtx& c, const std::vector<BatchItem>& items
     return PQB200_OK;
 }
 
-static int check_repeated_args(const double* a, size_t rows, size_t cols, size_t stride,
-                               const int64_t* row_mult, const int64_t* col_mult) {
-    if ((rows && !row_mult) || (cols && !col_mult)) return fail(PQB200_ERR_ARG, "multiplicity pointer is null");
-    if (rows && cols && !a) return fail(PQB200_ERR_ARG, "matrix pointer is null");
-    if (rows && cols && stride < cols) return fail(PQB200_ERR_ARG, "stride is smaller than the number of columns");
-    return PQB200_OK;
+// FP64 instructions of one repeated permanent with the given occupations (rough: the smaller Gray
+// space x 6 x photons); used only to choose the device count of an automatic call
+static double repeated_work(size_t rows, size_t cols, const int64_t* row_mult, const int64_t* col_mult) {
+    double sr = 1.0, sc = 1.0, n = 0.0;
+    for (size_t i = 0; i < rows; i++) if (row_mult[i] > 0) { sr *= (double)(row_mult[i] + 1); n += (double)row_mult[i]; }
+    for (size_t j = 0; j < cols; j++) if (col_mult[j] > 0) sc *= (double)(col_mult[j] + 1);
+    return std::min(sr, sc) * 6.0 * n;
 }
 
 int pqb200_permanent_repeated(const double* a, size_t rows, size_t cols, size_t stride,
@@ -809,12 +1095,11 @@ int pqb200_permanent_repeated(const double* a, size_t rows, size_t cols, size_t 
     if (!out) return fail(PQB200_ERR_ARG, "output pointer is null");
     int rc = check_repeated_args(a, rows, cols, stride, row_mult, col_mult);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(g_mu);
-    int used = 0;
-    rc = ensure_devices(ndev, &used);
+    Lease ls;
+    rc = acquire(ndev, repeated_work(rows, cols, row_mult, col_mult), ls);
     if (rc) return rc;
-    g_stats = {0.0, 0.0, 0, used};
-    return repeated_locked(a, rows, cols, stride, row_mult, col_mult, used, out);
+    g_stats = {0.0, 0.0, 0, ls.size()};
+    return ls.done(repeated_locked(ls, a, rows, cols, stride, row_mult, col_mult, out));
 }
 
 int pqb200_permanent_repeated_batch(const double* a, size_t rows, size_t cols, size_t stride,
@@ -822,16 +1107,12 @@ int pqb200_permanent_repeated_batch(const double* a, size_t rows, size_t cols, s
                                     size_t count, int ndev, double* out) {
     if (count && !out) return fail(PQB200_ERR_ARG, "output pointer is null");
     if (count == 0) return PQB200_OK;
-    std::lock_guard<std::mutex> lk(g_mu);
-    int used = 0;
-    int rc = ensure_devices(ndev, &used);
-    if (rc) return rc;
-    g_stats = {0.0, 0.0, 0, used};
     std::vector<BatchItem> items(count);
     std::vector<double> prefill(2 * count, 0.0);
     std::vector<size_t> too_big;
+    double work = 0.0;
     for (size_t k = 0; k < count; k++) {
-        rc = check_repeated_args(a, rows, cols, stride, row_mults + k * rows, col_mults + k * cols);
+        int rc = check_repeated_args(a, rows, cols, stride, row_mults + k * rows, col_mults + k * cols);
         if (rc) return rc;
         std::string err;
         BatchItem& it = items[k];
@@ -843,27 +1124,37 @@ int pqb200_permanent_repeated_batch(const double* a, size_t rows, size_t cols, s
         it.job.uoff = 0;
         if (it.kind == kJobTrivialOne) prefill[2 * k] = 1.0;
         else if (it.kind == kJobSingleRow) single_row_value(a, stride, it.job, &prefill[2 * k]);
-        else if (it.kind == kJobTooBig) too_big.push_back(k);
+        else if (it.kind == kJobTooBig) {
+            too_big.push_back(k);
+            work += repeated_work(rows, cols, row_mults + k * rows, col_mults + k * cols);
+        } else work += (double)it.job.len * (double)it.job.nchunks * 6.0 * it.job.N;
     }
+    Lease ls;
+    int rc = acquire(ndev, work, ls);
+    if (rc) return rc;
+    int used = ls.size();
+    g_stats = {0.0, 0.0, 0, used};
     // shard the items over the devices by contiguous ranges
     used = (int)std::min<size_t>((size_t)used, count);
     std::vector<std::vector<BatchItem>> per_dev((size_t)used);
     for (size_t k = 0; k < count; k++) per_dev[k * (size_t)used / count].push_back(items[k]);
-    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
-    CUDA_TRY(cudaEventRecord(g_devs[0].e0, g_devs[0].stream));
+    CUDA_TRY(cudaSetDevice(ls[0].dev));
+    CUDA_TRY(cudaEventRecord(ls[0].e0, ls[0].stream));
     for (int d = 0; d < used; d++) {
-        DeviceCtx& c = g_devs[d];
+        DeviceCtx& c = ls[d];
         CUDA_TRY(cudaSetDevice(c.dev));
-        rc = grow(&c.b_u, &c.b_u_cap, 16 * rows * stride);
-        if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(c.b_u, a, 16 * ((rows - 1) * stride + cols), cudaMemcpyHostToDevice, c.stream));
+        if (rows && cols) {
+            rc = grow(&c.b_u, &c.b_u_cap, 16 * rows * stride);
+            if (rc) return rc;
+            CUDA_TRY(cudaMemcpyAsync(c.b_u, a, 16 * ((rows - 1) * stride + cols), cudaMemcpyHostToDevice, c.stream));
+        }
         rc = run_batch_on_device(c, per_dev[(size_t)d], prefill, count);
         if (rc) return rc;
         if (d == 0) CUDA_TRY(cudaEventRecord(c.e1, c.stream));
     }
     std::vector<double> res(2 * count);
     for (int d = 0; d < used; d++) {
-        DeviceCtx& c = g_devs[d];
+        DeviceCtx& c = ls[d];
         CUDA_TRY(cudaSetDevice(c.dev));
         CUDA_TRY(cudaMemcpyAsync(res.data(), c.b_out, 16 * count, cudaMemcpyDeviceToHost, c.stream));
         CUDA_TRY(cudaStreamSynchronize(c.stream));
@@ -873,15 +1164,15 @@ int pqb200_permanent_repeated_batch(const double* a, size_t rows, size_t cols, s
         }
     }
     float ms = 0.f;
-    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
-    CUDA_TRY(cudaEventElapsedTime(&ms, g_devs[0].e0, g_devs[0].e1));
+    CUDA_TRY(cudaSetDevice(ls[0].dev));
+    CUDA_TRY(cudaEventElapsedTime(&ms, ls[0].e0, ls[0].e1));
     g_stats.kernel_ms = ms;
     // jobs whose Gray space is too large for one CTA use the grid-wide kernels, one at a time
     for (size_t k : too_big) {
-        rc = repeated_locked(a, rows, cols, stride, row_mults + k * rows, col_mults + k * cols, used, out + 2 * k);
+        rc = repeated_locked(ls, a, rows, cols, stride, row_mults + k * rows, col_mults + k * cols, out + 2 * k);
         if (rc) return rc;
     }
-    return PQB200_OK;
+    return ls.done(PQB200_OK);
 }
 
 int pqb200_permanent_batch(const double* const* a, const size_t* rows, const size_t* cols,
@@ -890,12 +1181,6 @@ int pqb200_permanent_batch(const double* const* a, const size_t* rows, const siz
     if (count == 0) return PQB200_OK;
     std::vector<size_t> single;  // matrices that do not fit one CTA (or are not square): grid-wide path
     {
-        std::lock_guard<std::mutex> lk(g_mu);
-        int used = 0;
-        int rc = ensure_devices(ndev, &used);
-        if (rc) return rc;
-        g_stats = {0.0, 0.0, 0, used};
-        DeviceCtx& c = g_devs[0];  // small matrices: one device is plenty (launch-latency bound)
         std::vector<BatchItem> items;
         std::vector<double> prefill(2 * count, 0.0), packed;
         const int64_t ones[kBatchColsMax] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1,
@@ -906,7 +1191,7 @@ int pqb200_permanent_batch(const double* const* a, const size_t* rows, const siz
                 single.push_back(k);
                 continue;
             }
-            rc = check_plain_args(a[k], n, n, strides[k]);
+            int rc = check_plain_args(a[k], n, n, strides[k]);
             if (rc) return rc;
             BatchItem it;
             memset(&it.job, 0, sizeof(it.job));
@@ -924,7 +1209,12 @@ int pqb200_permanent_batch(const double* const* a, const size_t* rows, const siz
                 packed.insert(packed.end(), a[k] + 2 * i * strides[k], a[k] + 2 * (i * strides[k] + n));
             items.push_back(it);
         }
+        g_stats = {0.0, 0.0, 0, 1};
         if (!items.empty()) {
+            Lease ls;
+            int rc = acquire(ndev <= 0 ? 0 : 1, 0.0, ls);  // small matrices: one device is plenty (launch-latency bound)
+            if (rc) return rc;
+            DeviceCtx& c = ls[0];
             CUDA_TRY(cudaSetDevice(c.dev));
             rc = grow(&c.b_u, &c.b_u_cap, sizeof(double) * packed.size());
             if (rc) return rc;
@@ -943,17 +1233,24 @@ int pqb200_permanent_batch(const double* const* a, const size_t* rows, const siz
             float ms = 0.f;
             CUDA_TRY(cudaEventElapsedTime(&ms, c.e0, c.e1));
             g_stats.kernel_ms = ms;
+            ls.done(PQB200_OK);
         }
     }
+    pqb200_stats acc = g_stats;
     for (size_t k : single) {
         int rc = pqb200_permanent(a[k], rows[k], cols[k], strides[k], ndev, out + 2 * k);
         if (rc) return rc;
+        acc.kernel_ms += g_stats.kernel_ms;
+        acc.gray_steps += g_stats.gray_steps;
+        acc.launches += g_stats.launches;
+        acc.ndev = std::max(acc.ndev, g_stats.ndev);
     }
+    g_stats = acc;
     return PQB200_OK;
 }
 
-// pmf rows for shots [s0, s1) on device c; async on c.stream, results left in c.b_pmf
-static int pmf_layer_on_device(DeviceCtx& c, const double* u, size_t m, size_t stride,
+// pmf rows for shots [s0, s1) on slot c; async on c.stream, results left in c.b_pmf
+static int pmf_layer_on_device(Lease& ls, DeviceCtx& c, const double* u, size_t m, size_t stride,
                                const int64_t* samples, const int64_t* inputs, size_t s0, size_t s1) {
     const size_t S = s1 - s0;
     const double t_begin = now_ms();
@@ -1020,16 +1317,20 @@ static int pmf_layer_on_device(DeviceCtx& c, const double* u, size_t m, size_t s
         if (t_rc[(size_t)t]) return fail(t_rc[(size_t)t], t_err[(size_t)t]);
         items.insert(items.end(), t_items[(size_t)t].begin(), t_items[(size_t)t].end());
         for (const TooBig& tb : t_big[(size_t)t]) {
-            // Gray space too large for one CTA: grid-wide kernels, synchronously
+            // Gray space too large for one CTA: grid-wide kernels on this slot, synchronously
             std::vector<int64_t> cols(inputs + tb.shot * m, inputs + (tb.shot + 1) * m);
             cols[tb.mode]--;
             double v[2];
-            const int rc = repeated_locked(u, m, m, stride, samples + tb.shot * m, cols.data(), 1, v);
+            Lease one;  // a view of this slot only (already locked by `ls`)
+            one.slots.push_back(&c);
+            const int rc = repeated_locked(one, u, m, m, stride, samples + tb.shot * m, cols.data(), v);
+            one.slots.clear();
             if (rc) return rc;
             prefill[2 * tb.slot] = v[0];
             prefill[2 * tb.slot + 1] = v[1];
         }
     }
+    (void)ls;
     const double t_jobs = now_ms();
     CUDA_TRY(cudaSetDevice(c.dev));
     int rc = grow(&c.b_u, &c.b_u_cap, 16 * m * stride);
@@ -1051,67 +1352,81 @@ static int pmf_layer_on_device(DeviceCtx& c, const double* u, size_t m, size_t s
     return PQB200_OK;
 }
 
-// caller holds g_mu
-static int pmf_layer_locked(const double* u, size_t m, size_t stride, const int64_t* samples,
-                            const int64_t* inputs, size_t S, int used, double* pmf) {
-    used = (int)std::min<size_t>((size_t)used, S);
+static int pmf_layer_locked(Lease& ls, const double* u, size_t m, size_t stride, const int64_t* samples,
+                            const int64_t* inputs, size_t S, double* pmf) {
+    const int used = (int)std::min<size_t>((size_t)ls.size(), S);
     const double t_layer = now_ms();
-    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
-    CUDA_TRY(cudaEventRecord(g_devs[0].e0, g_devs[0].stream));
+    CUDA_TRY(cudaSetDevice(ls[0].dev));
+    CUDA_TRY(cudaEventRecord(ls[0].e0, ls[0].stream));
     for (int d = 0; d < used; d++) {
         const size_t s0 = S * (size_t)d / (size_t)used, s1 = S * (size_t)(d + 1) / (size_t)used;
-        int rc = pmf_layer_on_device(g_devs[d], u, m, stride, samples, inputs, s0, s1);
+        int rc = pmf_layer_on_device(ls, ls[d], u, m, stride, samples, inputs, s0, s1);
         if (rc) return rc;
-        if (d == 0) CUDA_TRY(cudaEventRecord(g_devs[0].e1, g_devs[0].stream));
+        if (d == 0) CUDA_TRY(cudaEventRecord(ls[0].e1, ls[0].stream));
     }
     for (int d = 0; d < used; d++) {
-        DeviceCtx& c = g_devs[d];
+        DeviceCtx& c = ls[d];
         const size_t s0 = S * (size_t)d / (size_t)used, s1 = S * (size_t)(d + 1) / (size_t)used;
         CUDA_TRY(cudaSetDevice(c.dev));
         CUDA_TRY(cudaMemcpyAsync(pmf + s0 * m, c.b_pmf, sizeof(double) * (s1 - s0) * m, cudaMemcpyDeviceToHost, c.stream));
         CUDA_TRY(cudaStreamSynchronize(c.stream));
     }
     float ms = 0.f;
-    CUDA_TRY(cudaSetDevice(g_devs[0].dev));
-    CUDA_TRY(cudaEventElapsedTime(&ms, g_devs[0].e0, g_devs[0].e1));
+    CUDA_TRY(cudaSetDevice(ls[0].dev));
+    CUDA_TRY(cudaEventElapsedTime(&ms, ls[0].e0, ls[0].e1));
     g_stats.kernel_ms += ms;
     g_stats.ndev = used;
     if (trace_on()) fprintf(stderr, "[pqb200] pmf layer total %.2f ms (device-0 stream %.2f ms)\n", now_ms() - t_layer, ms);
     return PQB200_OK;
 }
 
-int pqb200_pmf_layer(const double* u, size_t m, size_t stride, const int64_t* samples,
-                     const int64_t* inputs, size_t S, int ndev, double* pmf) {
+static int check_pmf_args(const double* u, size_t m, size_t stride, const int64_t* samples,
+                          const int64_t* inputs, double* pmf) {
     if (!u || !samples || !inputs || !pmf) return fail(PQB200_ERR_ARG, "null pointer");
     if (m == 0 || m > 255) return fail(PQB200_ERR_ARG, "number of modes must be in 1..255");
     if (stride < m) return fail(PQB200_ERR_ARG, "stride is smaller than the number of modes");
-    if (S == 0) return PQB200_OK;
-    std::lock_guard<std::mutex> lk(g_mu);
-    int used = 0;
-    int rc = ensure_devices(ndev, &used);
+    return PQB200_OK;
+}
+
+static double max_photons(const int64_t* inputs, size_t S, size_t m) {
+    int64_t mx = 0;
+    for (size_t s = 0; s < S; s++) {
+        int64_t n = 0;
+        for (size_t i = 0; i < m; i++) n += inputs[s * m + i];
+        mx = std::max(mx, n);
+    }
+    return (double)mx;
+}
+
+int pqb200_pmf_layer(const double* u, size_t m, size_t stride, const int64_t* samples,
+                     const int64_t* inputs, size_t S, int ndev, double* pmf) {
+    int rc = check_pmf_args(u, m, stride, samples, inputs, pmf);
     if (rc) return rc;
-    g_stats = {0.0, 0.0, 0, used};
+    if (S == 0) return PQB200_OK;
+    Lease ls;
+    rc = acquire(ndev, laplace_work((double)S, max_photons(inputs, S, m)), ls);
+    if (rc) return rc;
+    g_stats = {0.0, 0.0, 0, ls.size()};
     // all sub-permanents of a shot in one Gray sweep (laplace_sampler.cuh); shots beyond that
     // kernel's photon limit fall through to one batched job per sub-permanent
-    rc = pmf_layer_laplace_locked(u, m, stride, samples, inputs, S, used, pmf);
-    if (rc != -1) return rc;
-    return pmf_layer_locked(u, m, stride, samples, inputs, S, used, pmf);
+    rc = pmf_layer_laplace_locked(ls, u, m, stride, samples, inputs, S, pmf);
+    if (rc != -1) return ls.done(rc);
+    return ls.done(pmf_layer_locked(ls, u, m, stride, samples, inputs, S, pmf));
 }
 
 // The same layer with one batched kernel job per sub-permanent (k repeated permanents per shot, as
 // compute_pmf itself does): kept as the cross-check of the single-sweep kernel and for > 40 photons.
 int pqb200_pmf_layer_batched(const double* u, size_t m, size_t stride, const int64_t* samples,
                              const int64_t* inputs, size_t S, int ndev, double* pmf) {
-    if (!u || !samples || !inputs || !pmf) return fail(PQB200_ERR_ARG, "null pointer");
-    if (m == 0 || m > 255) return fail(PQB200_ERR_ARG, "number of modes must be in 1..255");
-    if (stride < m) return fail(PQB200_ERR_ARG, "stride is smaller than the number of modes");
-    if (S == 0) return PQB200_OK;
-    std::lock_guard<std::mutex> lk(g_mu);
-    int used = 0;
-    int rc = ensure_devices(ndev, &used);
+    int rc = check_pmf_args(u, m, stride, samples, inputs, pmf);
     if (rc) return rc;
-    g_stats = {0.0, 0.0, 0, used};
-    return pmf_layer_locked(u, m, stride, samples, inputs, S, used, pmf);
+    if (S == 0) return PQB200_OK;
+    Lease ls;
+    const double ph = max_photons(inputs, S, m);
+    rc = acquire(ndev, ph * laplace_work((double)S, ph), ls);
+    if (rc) return rc;
+    g_stats = {0.0, 0.0, 0, ls.size()};
+    return ls.done(pmf_layer_locked(ls, u, m, stride, samples, inputs, S, pmf));
 }
 
 }  // extern "C"

@@ -20,15 +20,17 @@ void hl_plain_normalise(const double* a, int rows, int cols, size_t stride, int 
 
 // Prepares + normalises + plans one repeated permanent.  Returns <0 on error, 1 if trivial (value in
 // trivial_value), 2 if all multiplicities are 1 (plain route), 0 otherwise.  Caller-allocated
-// outputs: mat (R x N complex), r (R-1 ints), table_w / table_row / table_flags (len entries),
-// base (2 x N complex), radix, weight (R-1 entries), misc = {R, N, q, len, nchunks, lowpar0, lowpar1, photons}.
+// outputs: mat (R x C complex, columns NOT expanded), r (R-1 ints), cm (C ints), table_w / table_row /
+// table_flags (len entries), base (2 x C complex), radix, weight (R-1 entries), binom ((R-1) x 64),
+// misc = {R, C, q, len, nchunks, lowpar0, lowpar1, photons}.
 int hl_rep_plan(const double* a, size_t rows, size_t cols, size_t stride, const int64_t* row_mult,
                 const int64_t* col_mult, int max_len, int normalise, double* trivial_value, double* mat,
-                int* r, double* table_w, int* table_row, int* table_flags, double* base, int* radix,
+                int* r, int* cm, double* table_w, int* table_row, int* table_flags, double* base, int* radix,
                 unsigned long long* weight, double* binom, double* phase, long long* misc) {
     RepPrepared pr;
     std::string err;
-    int rc = rep_prepare(a, rows, cols, stride, row_mult, col_mult, 44, pr, err);
+    const RepLimits lim = {kPowMaxDigits, kPowMaxC, 254, kPowBufBytes, 32, 45};
+    int rc = rep_prepare(a, rows, cols, stride, row_mult, col_mult, lim, pr, err);
     if (rc) return -rc;
     if (pr.trivial) {
         trivial_value[0] = pr.value[0];
@@ -36,15 +38,16 @@ int hl_rep_plan(const double* a, size_t rows, size_t cols, size_t stride, const 
         return 1;
     }
     misc[0] = pr.R;
-    misc[1] = pr.N;
+    misc[1] = pr.C;
     misc[7] = pr.photons;
-    if (pr.all_single) {
+    for (int j = 0; j < pr.C; j++) cm[j] = pr.cm[j];
+    if (pr.plain_route) {
         memcpy(mat, pr.mat.data(), sizeof(double) * pr.mat.size());
         return 2;
     }
     if (normalise) rep_normalise(pr);
     RepPlan pl;
-    rep_plan(pr, 148 * 256, 1, (unsigned int)max_len, 45, pl);
+    rep_plan(pr, 148 * 256, 1, (unsigned int)max_len, 64, pl);
     memcpy(mat, pr.mat.data(), sizeof(double) * pr.mat.size());
     for (int d = 0; d < pr.R - 1; d++) {
         r[d] = pr.r[d];

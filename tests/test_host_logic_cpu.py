@@ -80,32 +80,35 @@ def _rep_plan(hl, U, inp, out, max_len, normalise=1):
     P = int(rm.sum())
     mat = np.zeros((P + 1, max(P, 1)), dtype=np.complex128)
     r = np.zeros(64, dtype=np.int32)
+    cmv = np.zeros(64, dtype=np.int32)
     tw = np.zeros(max_len + 1)
     trow = np.zeros(max_len + 1, dtype=np.int32)
     tfl = np.zeros(max_len + 1, dtype=np.int32)
     base = np.zeros((2, max(P, 1)), dtype=np.complex128)
     radix = np.zeros(64, dtype=np.int32)
     weight = np.zeros(64, dtype=np.uint64)
-    binom = np.zeros(64 * 45)
+    binom = np.zeros(64 * 64)
     phase = np.zeros(4)
     misc = np.zeros(8, dtype=np.int64)
     triv = np.zeros(2)
     rc = hl.hl_rep_plan(U.ctypes.data_as(_dp), ctypes.c_size_t(rows), ctypes.c_size_t(cols), ctypes.c_size_t(cols),
                         rm.ctypes.data_as(_lp), cm.ctypes.data_as(_lp), max_len, normalise, triv.ctypes.data_as(_dp),
-                        mat.ctypes.data_as(_dp), r.ctypes.data_as(_ip), tw.ctypes.data_as(_dp), trow.ctypes.data_as(_ip),
+                        mat.ctypes.data_as(_dp), r.ctypes.data_as(_ip), cmv.ctypes.data_as(_ip), tw.ctypes.data_as(_dp), trow.ctypes.data_as(_ip),
                         tfl.ctypes.data_as(_ip), base.ctypes.data_as(_dp), radix.ctypes.data_as(_ip),
                         weight.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), binom.ctypes.data_as(_dp),
                         phase.ctypes.data_as(_dp), misc.ctypes.data_as(_lp))
-    return rc, dict(mat=mat, r=r, tw=tw, trow=trow, tfl=tfl, base=base, radix=radix, weight=weight,
-                    binom=binom.reshape(64, 45), phase=complex(phase[0] + phase[1], phase[2] + phase[3]),
+    return rc, dict(mat=mat, r=r, cm=cmv, tw=tw, trow=trow, tfl=tfl, base=base, radix=radix, weight=weight,
+                    binom=binom.reshape(64, 64), phase=complex(phase[0] + phase[1], phase[2] + phase[3]),
                     R=int(misc[0]), N=int(misc[1]), q=int(misc[2]), len=int(misc[3]), nchunks=int(misc[4]),
                     lowpar=(int(misc[5]), int(misc[6])), photons=int(misc[7]), triv=complex(triv[0], triv[1]))
 
 
 def _emulate_repeated_kernel(pl):
-    """glynn_repeated_kernel in Python: one 'thread' per chunk, term t then the toggle of table entry t+1."""
+    """glynn_reppow_kernel in Python: one 'thread' per chunk, term t (product of the column sums raised
+    to their multiplicities) then the toggle of table entry t+1."""
     R, N, q, length = pl["R"], pl["N"], pl["q"], pl["len"]
     D = R - 1
+    cm = pl["cm"][:N].astype(np.int64)
     mat = pl["mat"].reshape(-1)[:R * N].reshape(R, N)
     A2 = 2.0 * mat
     total = 0.0
@@ -121,12 +124,12 @@ def _emulate_repeated_kernel(pl):
             whigh *= pl["binom"][d, k]
             ks[d] = k
         P = par
-        c = pl["base"][P, :N].copy()
+        c = pl["base"].reshape(-1)[:2 * N].reshape(2, N)[P].copy()
         for d in range(D - 1, q - 1, -1):
             c += 0.5 * (int(pl["radix"][d]) - 1 - 2 * ks[d]) * A2[d + 1]
         acc = 0.0
         for t in range(length):
-            acc += pl["tw"][t] * np.prod(c)
+            acc += pl["tw"][t] * np.prod(c ** cm)
             if t + 1 < length:
                 row, fl = int(pl["trow"][t + 1]), int(pl["tfl"][t + 1])
                 c += (-1.0 if (fl >> P) & 1 else 1.0) * A2[row]
@@ -141,6 +144,9 @@ def _emulate_repeated_kernel(pl):
     ([0, 4, 0, 3], [2, 2, 2, 1], 5),
     ([2, 2, 2, 2, 0, 0], [1, 1, 1, 1, 2, 2], 9),
     ([5, 0, 0, 0], [1, 1, 1, 2], 100),             # a single repeated column after transposition
+    ([6, 5, 0, 0], [4, 4, 3, 0], 50),              # power form: multiplicities up to 6 on both sides
+    ([3, 3, 3, 3], [12, 0, 0, 0], 20),             # one column twelve times
+    ([2, 2, 3, 1, 1, 0], [1, 1, 1, 2, 2, 2], 30),  # mixed multiplicities: sorted descending, largest last
 ])
 @pytest.mark.parametrize("normalise", [0, 1])
 def test_repeated_plan_tables_reproduce_the_reference(hl, case, normalise):
@@ -151,6 +157,8 @@ def test_repeated_plan_tables_reproduce_the_reference(hl, case, normalise):
     rc, pl = _rep_plan(hl, U, inp, out, max_len, normalise)
     assert rc == 0, rc
     assert pl["len"] <= max_len
+    cm = pl["cm"][:pl["N"]]
+    assert cm.sum() == pl["photons"] and cm[-1] == cm.max() and np.all(np.diff(cm[:-1]) <= 0)
     if normalise:
         mat = pl["mat"].reshape(-1)[:pl["R"] * pl["N"]].reshape(pl["R"], pl["N"])
         assert np.all(mat[1].imag == 0.0) and np.all(mat[:, -1].imag == 0.0)
