@@ -8,9 +8,11 @@ partials combined with one NCCL all-gather of 4 doubles per rank.
 Prints ONE JSON line (rank 0).  `value` = Gray steps per second of the whole job (inputs resident:
 the matrix travels as 25.6 KB of kernel parameters, there is nothing else to stage); `e2e` = the same
 through the public host API (numpy in, complex out) with the host->device parameter copy and the
-device->host read of the result inside the timed region; `roofline` compares the kernel's
-algorithmic FP64 flop rate (8n per Gray step) with the FP64 pipe peak measured live by
-pqb200_fp64_peak (MEASURED_PEAKS.json has no FP64 entry); `cpu_baseline` times the UNMODIFIED
+device->host read of the result inside the timed region -- GlynnPermanentCalculator_wrapper(...,
+ndev=1) on one GPU, distributed.permanent_nccl on every rank for N > 1; `roofline` compares the
+kernel's algorithmic FP64 flop rate (8n per Gray step) with the FP64 pipe peak (SMs x 64 lanes x 2 x
+the SM clock sampled under load; MEASURED_PEAKS.json has no FP64 entry); `configs` carries the other
+BASELINE.json configs (C1, C2, C4, C5) measured in the same run; `cpu_baseline` times the UNMODIFIED
 reference BBFGPermanentCalculator (oracle/_ref, TBB shim, all host cores) on a bounded sample.
 `--impl reference` runs only that CPU arm, in the same units.
 """
@@ -223,17 +225,29 @@ def run_b200(args, rank, local_rank, world):
     kernel_ms = k0.elapsed_time(k1) / kreps
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end to end through the public host API: numpy in -> complex out, every step
+    # ---- end to end through the PUBLIC host API: numpy in -> complex out, every step.
+    #      1 GPU : GlynnPermanentCalculator_wrapper(A, lib, ndev=1).calculate()  (exactly this rank's device)
+    #      N GPUs: distributed.permanent_nccl(A) on every rank (pqb200_permanent_nccl: shard kernel +
+    #              ncclAllGather + host fold inside the library)
+    from piquassoboost_b200.distributed import permanent_nccl
+
+    def e2e_call():
+        if world == 1:
+            return pqb.GlynnPermanentCalculator_wrapper(A_np, pqb.GlynnB200, ndev=1).calculate()
+        return permanent_nccl(A_np)
+
+    small = haar(16)
+    if world == 1:
+        pqb.GlynnPermanentCalculator_wrapper(small, pqb.GlynnB200, ndev=1).calculate()   # warm the path (slot, module)
+    else:
+        permanent_nccl(small)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        if world == 1:
-            e2e_val = pqb.GlynnPermanent(A_np).calculate()           # host buffers in, host result out
-        else:
-            step()
-            e2e_val = result()                                        # device->host read of the partials
+        e2e_val = e2e_call()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    e2e_ndev = pqb.last_stats()["ndev"]
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
@@ -241,22 +255,35 @@ def run_b200(args, rank, local_rank, world):
     if rank == 0:
         steps_per_perm = 2.0 ** (n - 1)
         value = steps_per_perm * args.steps / (total_ms * 1e-3)
-        # FP64 roofline: measured DFMA issue rate x 2 flop
-        peak = ctypes.c_double(0.0)
-        _lib.check(lib.pqb200_fp64_peak(local_rank, 0, 0.25, ctypes.byref(peak)))
+        # FP64 roofline.  Denominator: the FP64 pipe's peak = SMs x 64 lanes x 2 flop x the SM clock measured
+        # under load during the timed region (MEASURED_PEAKS.json has no FP64 entry; the profiling guide
+        # states no FP64 fallback).  The live issue-rate measurement of pqb200_fp64_peak is printed beside it.
+        props = torch.cuda.get_device_properties(local_rank)
+        sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+        peak_tflops = props.multi_processor_count * 64 * 2 * sm_mhz * 1e6 / 1e12
+        dfma = ctypes.c_double(0.0)
+        _lib.check(lib.pqb200_fp64_peak(local_rank, 0, 0.25, ctypes.byref(dfma)))
         dadd = ctypes.c_double(0.0)
         _lib.check(lib.pqb200_fp64_peak(local_rank, 1, 0.25, ctypes.byref(dadd)))
-        peak_tflops = 2.0 * peak.value / 1e12
         shard_steps = steps_per_perm / world
         achieved = 8.0 * n * shard_steps / (kernel_ms * 1e-3) / 1e12
-        # small parity gate inside the same run (the n=40 value itself has no affordable CPU truth)
+        instr_per_step = 5.5 * n - 6.5
+        # small parity gates inside the same run (the n=40 value itself has no affordable CPU truth)
         from oracle import oraclebind, refbind
-        B = haar(18)
-        got = pqb.GlynnPermanent(B).calculate()
-        want = refbind.bbfg(B, True) if refbind.available() else oraclebind.bbfg(B, oraclebind.LONG_DOUBLE)
+
+        def cpu_truth(M):
+            return refbind.bbfg(M, True) if refbind.available() else oraclebind.bbfg(M, oraclebind.LONG_DOUBLE)
+
+        parity = []
+        for pn in (18, 24):
+            B = haar(pn)
+            got = pqb.GlynnPermanentCalculator_wrapper(B, pqb.GlynnB200, ndev=1).calculate()
+            want = cpu_truth(B)
+            parity.append({"n": pn, "rel_err_vs_long_double_reference": abs(got - want) / abs(want), "tolerance": 1e-10})
         cpu_equiv, cpu_desc, _ = cpu_reference_rate(n, args.cpu_seconds)
-        # the value of THIS run's permanent against the committed double-double evaluation (itself
-        # pinned to the reference's long double up to n=36; tests/golden/plain_dd_reference.json)
+        # the value of THIS run's permanent against the committed golden values: the reference's own long
+        # double where one exists (n <= 38, tools/ref_big.py), else the double-double evaluation (itself
+        # pinned to the reference's long double up to n=38; tests/golden/plain_dd_reference.json)
         accuracy = None
         try:
             gold = json.load(open(os.path.join(ROOT, "tests", "golden", "plain_dd_reference.json")))["cases"]
@@ -266,6 +293,7 @@ def run_b200(args, rank, local_rank, world):
                             "tolerance": 1e-10, "golden": "tests/golden/plain_dd_reference.json"}
         except OSError:
             pass
+        traffic, traffic_src = ncu_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -278,30 +306,134 @@ def run_b200(args, rank, local_rank, world):
                        "l2_note": "working set is 25.6 KB of kernel parameters + registers; no HBM traffic to flush"},
             "seconds_per_permanent": total_ms / args.steps * 1e-3,
             "permanent": [value_perm.real, value_perm.imag],
-            "parity_check": {"n": 18, "rel_err_vs_long_double_reference": abs(got - want) / abs(want),
-                             "tolerance": 1e-10},
+            "parity_check": parity,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tflops, "traffic": 80896,
-                         "peak_source": "measured live: pqb200_fp64_peak DFMA chains x 2 flop "
-                                        f"(DADD-only issue rate {dadd.value / 1e12:.2f} T thread-instr/s; "
-                                        "nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2)",
+                         "frac": achieved / peak_tflops, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": f"{props.multi_processor_count} SMs x 64 FP64 lanes x 2 flop x {sm_mhz:.0f} MHz "
+                                        "(median SM clock sampled during the timed region)",
+                         "measured_issue_rates": {
+                             "dfma_tflops": 2.0 * dfma.value / 1e12, "dadd_thread_instr_per_s": dadd.value,
+                             "note": "pqb200_fp64_peak: independent DFMA / DADD chains, 2 CTAs x 256 threads per SM"},
                          "algorithmic_flops_per_step": 8 * n, "kernel_ms": kernel_ms,
                          # FP64 instructions per Gray step after the real-row/real-column normalisation:
                          # 5.5n - 6.5; each issues at most 1 FMA = 2 flop
-                         "instruction_mix_ceiling": (8.0 * n) / (2.0 * (5.5 * n - 6.5))},
+                         "fp64_instr_per_step": instr_per_step,
+                         "fp64_pipe_utilisation": instr_per_step * shard_steps / (kernel_ms * 1e-3)
+                                                  / (props.multi_processor_count * 64 * sm_mhz * 1e6),
+                         "instruction_mix_ceiling": (8.0 * n) / (2.0 * instr_per_step)},
             "accuracy": accuracy,
             "cpu_baseline": cpu_desc,
             "e2e": {"value": steps_per_perm * args.steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": 16 * n * n * world, "d2h_bytes_per_step": 32 * world,
                     "seconds_per_permanent": e2e_s / args.steps,
+                    "api": ("GlynnPermanentCalculator_wrapper(A, GlynnB200, ndev=1).calculate()" if world == 1
+                            else "distributed.permanent_nccl(A) on every rank"),
+                    "devices_used_per_process": e2e_ndev,
                     "permanent": [e2e_val.real, e2e_val.imag]},
             "gpu_launches": args.steps * world,
             "clocks": clocks,
         }
+        if not args.no_configs:
+            line["configs"] = baseline_configs(pqb, world, cpu_truth, props.multi_processor_count * 64 * sm_mhz * 1e6)
         print(json.dumps(line), flush=True)
     if world > 1:
+        # the other ranks wait on the CPU (a NCCL barrier would park a spinning kernel on their GPUs
+        # while rank 0 runs the C5 side measurement over all devices of the box)
+        import datetime
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set("pqb200_bench_done", "1")
+        else:
+            store.wait(["pqb200_bench_done"], datetime.timedelta(minutes=30))
         nccl_shutdown()
         dist.destroy_process_group()
+
+
+def ncu_traffic():
+    """dram bytes (read + write) per launch of the headline kernel from the committed ncu --set full
+    capture of this round's kernel (profiles/); (None, reason) when no capture is committed."""
+    import csv
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_plain40_r*_raw.csv")), reverse=True):
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr = rows[0]
+            ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            units, data = rows[1], [r for r in rows[2:] if len(r) > max(ir, iw)]
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            tot = [float(r[ir].replace(",", "")) * scale.get(units[ir], 1.0)
+                   + float(r[iw].replace(",", "")) * scale.get(units[iw], 1.0) for r in data]
+            if tot:
+                return sum(tot) / len(tot), f"ncu --set full capture {os.path.relpath(path, ROOT)} (dram read + write per launch)"
+        except (OSError, ValueError, IndexError):
+            continue
+    return None, "no ncu capture committed under profiles/"
+
+
+def baseline_configs(pqb, world, cpu_truth, fp64_instr_peak):
+    """The other BASELINE.json configs in the same run (rank 0, after the timed region): C1 n=20, C2 n=30,
+    C4 30 photons / 60 modes, C5 20 photons / 40 modes / 1000 shots -- through the public classes, wall
+    clock per call (host buffers in and out), kernel time from the library's CUDA events, parity against
+    the CPU reference where that takes seconds.  C5 shards its shots over all `world` GPUs of the box from
+    this one process (the `ndev` route; no collective)."""
+    from scipy.stats import unitary_group
+    from oracle import oraclebind, refbind
+    out = {}
+
+    def timed(fn, reps):
+        fn()
+        t = time.perf_counter()
+        for _ in range(reps):
+            v = fn()
+        return v, (time.perf_counter() - t) / reps
+
+    for tag, pn in (("C1_n20", 20), ("C2_n30", 30)):
+        M = haar(pn)
+        v, sec = timed(lambda: pqb.GlynnPermanentCalculator_wrapper(M, pqb.GlynnB200, ndev=1).calculate(), 5)
+        st = pqb.last_stats()
+        entry = {"seconds_per_call": sec, "kernel_ms": st["kernel_ms"], "gray_steps_per_s": st["gray_steps"] / sec,
+                 "fp64_pipe_utilisation_kernel": (5.5 * pn - 6.5) * st["gray_steps"] / (st["kernel_ms"] * 1e-3) / fp64_instr_peak}
+        if pn <= 26 or refbind.available():
+            t = time.perf_counter()
+            want = cpu_truth(M)
+            entry["reference_long_double_s"] = time.perf_counter() - t
+            entry["rel_err"] = abs(v - want) / abs(want)
+        out[tag] = entry
+    U = np.ascontiguousarray(unitary_group.rvs(60, random_state=4))
+    rng = np.random.default_rng(4)
+    inp = np.array([1] * 30 + [0] * 30)
+    cases = {"15x2": np.array([2] * 15 + [0] * 45), "10x3": np.array([3] * 10 + [0] * 50),
+             "multinomial": rng.multinomial(30, rng.dirichlet(np.ones(60) * 0.3))}
+    for name, o in cases.items():
+        v, sec = timed(lambda: pqb.ChinHuhPermanentCalculator_wrapper(pqb.GlynnRepB200, U, inp, o, ndev=1).calculate(), 5)
+        st = pqb.last_stats()
+        entry = {"seconds_per_call": sec, "kernel_ms": st["kernel_ms"], "gray_steps": st["gray_steps"]}
+        if refbind.available():
+            t = time.perf_counter()
+            want = refbind.bbfg_repeated(U, inp, o, True)
+            entry["reference_long_double_s"] = time.perf_counter() - t
+            entry["rel_err"] = abs(v - want) / abs(want)
+        out["C4_30ph_60modes_" + name] = entry
+    V = np.ascontiguousarray(unitary_group.rvs(40, random_state=5))
+    state = np.array([1] * 20 + [0] * 20, dtype=np.int64)
+    for shots in (1000, 20000):
+        for nd in sorted({1, world}):
+            sim = pqb.GeneralizedCliffordsBSimulationStrategy(V, seed=5, ndev=nd)
+            sim.simulate(state, shots)       # first call on these devices: contexts, buffers
+            sim.seed(5)
+            t = time.perf_counter()
+            res = sim.simulate(state, shots)
+            sec = time.perf_counter() - t
+            st = pqb.last_stats()
+            entry = {"shots": shots, "gpus": st["ndev"], "seconds_per_call": sec, "shots_per_s": shots / sec,
+                     "kernel_ms_device0": st["kernel_ms"], "gray_terms": st["gray_steps"], "launches": st["launches"]}
+            if shots == 1000 and refbind.available():
+                t = time.perf_counter()
+                want = refbind.simulate_B(V, 5, state, 20)
+                entry["reference_s_per_shot"] = (time.perf_counter() - t) / 20
+                entry["first_20_shots_identical_to_reference"] = bool(np.array_equal(np.array(res[:20]), want))
+            out[f"C5_20ph_40modes_{shots}shots_{nd}gpu"] = entry
+    return out
 
 
 def main():
@@ -313,6 +445,7 @@ def main():
     ap.add_argument("--size", dest="n", type=int, default=40, help="matrix size (BASELINE config C3 = 40)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
     ap.add_argument("--ref-step-seconds", type=float, default=6.0, help="--impl reference: per-step budget")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1/C2/C4/C5 side measurements")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

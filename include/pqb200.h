@@ -134,7 +134,7 @@ int pqb200_permanent_batch(const double* const* a, const size_t* rows, const siz
  * no photon-number cap; the limits are 45 distinct rows x 48 distinct columns on the two sides after
  * the orientation choice, and multiplicities <= 254.
  * Precision dispatch: the kernel also returns sum|term|; when the a-posteriori rounding bound
- * eps*(photons+8)*sum|term|/|sum| exceeds 2e-8 the call is re-evaluated in double-double arithmetic
+ * eps*(photons+8)*sum|term|/|sum| exceeds 2e-9 the call is re-evaluated in double-double arithmetic
  * (pqb200_permanent_repeated_dd) -- the engine's form of the reference's use_extended / use_inf
  * dispatch (BBFGPermanentCalculatorRepeated.cpp:105-141).  pqb200_last_repeated_bound reports the
  * bound of the calling thread's most recent repeated permanent and whether it was re-evaluated. */

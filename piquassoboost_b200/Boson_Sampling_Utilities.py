@@ -14,6 +14,7 @@ of the engine (FP64 products, double-double accumulation; SURVEY.md Appendix A.4
 their meaning only as far as "which reference calculator would have been used".
 """
 import ctypes
+import sys
 
 import numpy as np
 
@@ -52,7 +53,8 @@ _PLAIN_LIBS = {GlynnRep, GlynnDouble, BBFGDouble, BBFGLongDouble, GlynnSimpleDou
 _REPEATED_LIBS = {ChinHuh, GlynnRepLongDouble, GlynnRepDouble, BBFGRepDouble, BBFGRepLongDouble,
                   GlynnRepB200}
 
-#: number of GPUs one calculate() call is sharded over (0 = all devices the library sees)
+#: number of GPUs one calculate() call is sharded over (0 = automatic: as many devices as the call's
+#: work is worth -- small permanents run on one GPU, see include/pqb200.h)
 DEFAULT_NDEV = 0
 
 
@@ -116,6 +118,20 @@ class GlynnPermanentCalculator_wrapper:
             raise Pqb200Error("Wrong value set for permanent library.")
         if self._matrix is None:
             raise Pqb200Error("matrix is not set")
+        if self.lib in (GlynnSimpleDouble, GlynnSimpleLongDouble):
+            # GlynnPermanentCalculatorSimple only takes square matrices: it prints the message below and
+            # returns 0 otherwise (GlynnPermanentCalculatorSimple.hpp:67-70)
+            mats = self._matrix if isinstance(self._matrix, list) else [self._matrix]
+            if any(m.shape[0] != m.shape[1] for m in mats):
+                vals = []
+                for m in mats:
+                    if m.shape[0] != m.shape[1]:
+                        print("Error: GlynnPermanentCalculatorSimple only works for square matrices",
+                              file=sys.stderr)
+                        vals.append(0j)
+                    else:
+                        vals.append(_plain_permanent(m, self.ndev))
+                return vals if isinstance(self._matrix, list) else vals[0]
         if isinstance(self._matrix, list):
             return self._calculate_list(self._matrix)
         return _plain_permanent(self._matrix, self.ndev)
@@ -137,8 +153,11 @@ class GlynnPermanentCalculator_wrapper:
 
 class ChinHuhPermanentCalculator_wrapper:
     """Mirror of the CPython type of the same name: `(lib, matrix, input_state, output_state)`.
-    States may be lists of arrays: the result is then a nested list [input][output]
-    (ChinHuhPermanentCalculator_Wrapper.hpp:233-326)."""
+    List-valued states follow the reference (ChinHuhPermanentCalculator_Wrapper.hpp:233-326): a list
+    of n input vectors with a list of n (ragged) lists of output vectors -- or the other way round --
+    gives ret[i][j]; two flat lists give the full cross product (extension, see `_pairs`).
+    lib 0 (ChinHuh: the reference's Ryser-type CChinHuhPermanentCalculator) is served by the same
+    Glynn/BBFG engine -- the value is the same permanent, only the reference's algorithm differs."""
 
     def __init__(self, lib=BBFGRepDouble, matrix=None, input_state=None, output_state=None,
                  ndev=None):
@@ -150,34 +169,92 @@ class ChinHuhPermanentCalculator_wrapper:
 
     @staticmethod
     def _norm_state(state):
+        """None, one occupation vector, a flat list of vectors, or a list of lists of vectors (the
+        reference's per-input / per-output form, ChinHuhPermanentCalculator_Wrapper.hpp:233-263)."""
         if state is None:
             return None
-        if isinstance(state, list) and len(state) and isinstance(state[0], np.ndarray):
-            return [_lib.as_state(s) for s in state]
+        if isinstance(state, (list, tuple)):
+            if len(state) == 0:
+                return []
+            if all(isinstance(s, np.ndarray) for s in state):
+                return [_lib.as_state(s) for s in state]                        # flat list of vectors
+            if all(isinstance(inner, (list, tuple)) and all(isinstance(s, np.ndarray) for s in inner)
+                   for inner in state):
+                return [[_lib.as_state(s) for s in inner] for inner in state]   # list of (ragged) lists
         return _lib.as_state(state)
+
+    @staticmethod
+    def _is_nested(state):
+        return isinstance(state, list) and len(state) > 0 and isinstance(state[0], list)
+
+    def _pairs(self):
+        """(input, output) occupation pairs of a list-valued call and the shape of the result.
+
+        Reference forms (ChinHuhPermanentCalculator_Wrapper.hpp:233-326): `input_state` a list of n
+        vectors and `output_state` a list of n lists of vectors -> ret[i][j] = perm(input[i],
+        output[i][j]); or the other way round ("multiInput": `input_state` a list of lists, one per
+        output vector).  Extension of this package: two FLAT lists -> the full cross product
+        ret[i][o] (what piquasso's batched connector call needs)."""
+        ins, outs = self.input_state, self.output_state
+        if self._is_nested(ins) and not self._is_nested(outs):
+            outs = outs if isinstance(outs, list) else [outs]
+            if len(ins) != len(outs):
+                raise Pqb200Error("input_state (list of lists) and output_state must have the same length")
+            return [(i, outs[k]) for k, inner in enumerate(ins) for i in inner], [len(inner) for inner in ins]
+        if self._is_nested(outs):
+            ins = ins if isinstance(ins, list) else [ins]
+            if len(ins) != len(outs):
+                raise Pqb200Error("input_state and output_state (list of lists) must have the same length")
+            return [(ins[k], o) for k, inner in enumerate(outs) for o in inner], [len(inner) for inner in outs]
+        ins = ins if isinstance(ins, list) else [ins]
+        outs = outs if isinstance(outs, list) else [outs]
+        return None, (ins, outs)
 
     def calculate(self):
         if self.lib not in _REPEATED_LIBS:
             if self.lib in (GlynnRepSingleDFE, GlynnRepDualDFE, GlynnRepMultiSingleDFE,
                             GlynnRepMultiDualDFE, 10, 11):
                 raise Pqb200Error("DFE (FPGA) permanent calculators are not part of this build")
-            if self.lib == GlynnRepInf:
-                # the reference needs an MPFR build for this id (BBFGPermanentCalculatorRepeated.cpp:117-124);
-                # here it is served by the extended mode (every operation in double-double)
-                ins, outs = self.input_state, self.output_state
-                if isinstance(ins, list) or isinstance(outs, list):
-                    ins = ins if isinstance(ins, list) else [ins]
-                    outs = outs if isinstance(outs, list) else [outs]
-                    return [[permanent_repeated_double_double(self.matrix, i, o, self.ndev)[0] for o in outs]
-                            for i in ins]
-                return permanent_repeated_double_double(self.matrix, ins, outs, self.ndev)[0]
-            raise Pqb200Error("Wrong value set for permanent library.")
+            if self.lib != GlynnRepInf:
+                raise Pqb200Error("Wrong value set for permanent library.")
         ins, outs = self.input_state, self.output_state
         if isinstance(ins, list) or isinstance(outs, list):
-            ins = ins if isinstance(ins, list) else [ins]
-            outs = outs if isinstance(outs, list) else [outs]
-            return self._calculate_lists(ins, outs)
+            pairs, shape = self._pairs()
+            if pairs is None:
+                cross_ins, cross_outs = shape
+                if self.lib == GlynnRepInf:
+                    return [[permanent_repeated_double_double(self.matrix, i, o, self.ndev)[0] for o in cross_outs]
+                            for i in cross_ins]
+                return self._calculate_lists(cross_ins, cross_outs)
+            if self.lib == GlynnRepInf:
+                flat = [permanent_repeated_double_double(self.matrix, i, o, self.ndev)[0] for i, o in pairs]
+            else:
+                flat = self._calculate_pairs(pairs)
+            ret, pos = [], 0
+            for n in shape:
+                ret.append(flat[pos:pos + n])
+                pos += n
+            return ret
+        if self.lib == GlynnRepInf:
+            # the reference needs an MPFR build for this id (BBFGPermanentCalculatorRepeated.cpp:117-124);
+            # here it is served by the extended mode (every operation in double-double)
+            return permanent_repeated_double_double(self.matrix, ins, outs, self.ndev)[0]
         return _repeated_permanent(self.matrix, ins, outs, self.ndev)
+
+    def _calculate_pairs(self, pairs):
+        m = self.matrix
+        count = len(pairs)
+        if count == 0:
+            return []
+        cols = np.ascontiguousarray(np.array([p[0] for p in pairs], dtype=np.int64).reshape(count, -1))
+        rows = np.ascontiguousarray(np.array([p[1] for p in pairs], dtype=np.int64).reshape(count, -1))
+        if cols.shape[1] != m.shape[1] or rows.shape[1] != m.shape[0]:
+            raise Pqb200Error("state lengths do not match the matrix shape")
+        out = np.zeros(2 * count, dtype=np.float64)
+        _lib.check(_lib.load().pqb200_permanent_repeated_batch(
+            _lib.dptr(m), m.shape[0], m.shape[1], m.strides[0] // 16 if m.shape[1] else 0, _lib.iptr(rows),
+            _lib.iptr(cols), count, self.ndev, _lib.dptr(out)))
+        return out.view(np.complex128).tolist()
 
     def _calculate_lists(self, ins, outs):
         m = self.matrix
@@ -207,7 +284,7 @@ class RepeatedPermanentCalculator(ChinHuhPermanentCalculator_wrapper):
             elif any(not isinstance(item, np.ndarray) for item in input_state):
                 if all(np.isscalar(item) for item in input_state):
                     input_state = np.array(input_state, dtype=np.int64)
-                else:
+                elif not all(isinstance(item, list) for item in input_state):
                     raise Exception('The input state should be a numpy array, or a list of numpy arrays')
         if not isinstance(output_state, np.ndarray):
             if not isinstance(output_state, list):
@@ -215,7 +292,7 @@ class RepeatedPermanentCalculator(ChinHuhPermanentCalculator_wrapper):
             elif any(not isinstance(item, np.ndarray) for item in output_state):
                 if all(np.isscalar(item) for item in output_state):
                     output_state = np.array(output_state, dtype=np.int64)
-                else:
+                elif not all(isinstance(item, list) for item in output_state):
                     raise Exception('The output state should be a numpy array, or a list of numpy arrays')
         super().__init__(lib=lib, matrix=matrix, input_state=input_state, output_state=output_state)
 

@@ -74,54 +74,96 @@ struct PowParams {
 __host__ __device__ constexpr int pow_group(int c) { return c - 1 >= 4 ? 4 : c - 1 >= 2 ? 2 : 1; }
 // resident CTAs per SM the register budget is set for (measured: tools/rep_cases.py)
 #ifndef PQB_POW_MINB
-#define PQB_POW_MINB(c) ((c) <= 12 ? 3 : (c) <= 26 ? 2 : 1)
+#define PQB_POW_MINB(c) ((c) <= 8 ? 3 : (c) <= 26 ? 2 : 1)
 #endif
 __host__ __device__ constexpr int pow_min_blocks(int c) { return PQB_POW_MINB(c); }
+// multiply chains of the straight-line form (measured on C4-shaped problems: the count matters little)
+__host__ __device__ constexpr int pow_chains(int c) { return c >= 36 ? 4 : c >= 4 ? 2 : 1; }
 
 template <int C>
 __device__ __forceinline__ double2 pow_elem(const PowParams<C>& p, int row, int j) {
     return p.buf.c[row * pow_row_stride(C) + j];
 }
 
-// One weighted term, acc += w * prod_j c[j]^cm[j], fused with the toggle of row `row` into the next
-// term.  Columns 0..C-2 are complex, column C-1 is real.  The columns are handled in groups of G: the
-// G powers of a group are independent multiply chains (instruction-level parallelism), each group is
-// folded into one of G running products, and the previous group's columns are toggled while the
-// current group's powers are formed (their old values are dead by then).
+#ifndef PQB_POW_LAG
+#define PQB_POW_LAG 4
+#endif
+
+// One weighted term, acc += w * prod_j c[j], fused with the toggle of row `row` into the next term --
+// the form for product sides WITHOUT repeated columns (every cm[j] == 1: the C4 shape, Gray side
+// repeated, product side single): one straight-line block, CH multiply chains, the toggle of column
+// j issued PQB_POW_LAG columns behind the chain multiply that last used it (the row index comes out
+// of the step table, the row loads depend on it and a warp issues in order -- the first toggle must
+// not sit at the top of the term).  Columns 0..C-2 are complex, column C-1 is real.
 template <int C, bool REALROW>
-__device__ __forceinline__ void pow_term_toggle(const PowParams<C>& p, int row, double sg, double w,
-                                                double (&cr)[C], double (&ci)[C], double& acc_re,
-                                                double& acc_im, double& acc_abs) {
+__device__ __forceinline__ void pow_term_toggle_single(const PowParams<C>& p, int row, double sg, double w,
+                                                       double (&cr)[C], double (&ci)[C], double& acc_re,
+                                                       double& acc_im, double& acc_abs) {
+    constexpr int M = C - 1;  // complex factors; column C-1 is real
+    constexpr int CH0 = pow_chains(C);
+    constexpr int CH = M == 0 ? 1 : (CH0 < M ? CH0 : M);
+    constexpr int LAG = PQB_POW_LAG;
+    double qr[CH], qi[CH];
+    if constexpr (M == 0) {
+        qr[0] = 1.0;
+        qi[0] = 0.0;
+    } else {
+#pragma unroll
+        for (int k = 0; k < CH; k++) {
+            qr[k] = cr[k];
+            qi[k] = ci[k];
+        }
+#pragma unroll
+        for (int j = CH; j < M; j++) {
+            cmul(qr[j % CH], qi[j % CH], cr[j], ci[j]);
+            if (j - LAG >= 0) {
+                const double2 a = pow_elem<C>(p, row, j - LAG);
+                cr[j - LAG] = fma(sg, a.x, cr[j - LAG]);
+                if (!REALROW) ci[j - LAG] = fma(sg, a.y, ci[j - LAG]);
+            }
+        }
+#pragma unroll
+        for (int v = 1; v < CH; v *= 2) {
+#pragma unroll
+            for (int k = 0; k + v < CH; k += 2 * v) cmul(qr[k], qi[k], qr[k + v], qi[k + v]);
+        }
+    }
+    const double f = w * cr[C - 1];
+    if constexpr (M > 0) {
+#pragma unroll
+        for (int j = (M - LAG > 0 ? M - LAG : 0); j < M; j++) {
+            const double2 a = pow_elem<C>(p, row, j);  // the columns the chain loop has not toggled yet
+            cr[j] = fma(sg, a.x, cr[j]);
+            if (!REALROW) ci[j] = fma(sg, a.y, ci[j]);
+        }
+    }
+    cr[C - 1] = fma(sg, pow_elem<C>(p, row, C - 1).x, cr[C - 1]);
+    acc_re = fma(qr[0], f, acc_re);
+    acc_im = fma(qi[0], f, acc_im);
+    acc_abs = fma(fabs(qr[0]) + fabs(qi[0]), fabs(f), acc_abs);
+}
+
+// The general form, acc += w * prod_j c[j]^cm[j]: the complex columns are handled in groups of G, one
+// running product per position in the group (G independent multiply chains); column sum j is
+// multiplied into its chain cm[j] times (BBFGPermanentCalculatorRepeated.hpp:263-275).  The columns
+// are sorted by descending multiplicity, so the first column of a group carries the group's trip
+// count and the others are predicated (uniformly) only where multiplicities differ.  The previous
+// group's columns are toggled while the current group is multiplied (their old values are dead).
+template <int C, bool REALROW>
+__device__ __forceinline__ void pow_term_toggle_general(const PowParams<C>& p, int row, double sg, double w,
+                                                        double (&cr)[C], double (&ci)[C], double& acc_re,
+                                                        double& acc_im, double& acc_abs) {
     constexpr int M = C - 1;  // complex columns
     constexpr int G = pow_group(C);
     double qr[G], qi[G];
 #pragma unroll
     for (int u = 0; u < G; u++) {
-        qr[u] = 1.0;
-        qi[u] = 0.0;
+        qr[u] = u < M ? cr[u] : 1.0;
+        qi[u] = u < M ? ci[u] : 0.0;
     }
 #pragma unroll
     for (int g0 = 0; g0 < M; g0 += G) {
-        double pr[G], pi[G];
-#pragma unroll
-        for (int u = 0; u < G; u++)
-            if (g0 + u < M) {
-                pr[u] = cr[g0 + u];
-                pi[u] = ci[g0 + u];
-            }
         const int mmax = p.cm[g0];  // the largest multiplicity of the group (columns are sorted)
-        if (mmax > 1) {
-#pragma unroll 1
-            for (int k = 1; k < mmax; k++) {
-#pragma unroll
-                for (int u = 0; u < G; u++)
-                    if (g0 + u < M) {
-                        if (u == 0 || k < (int)p.cm[g0 + u]) cmul(pr[u], pi[u], cr[g0 + u], ci[g0 + u]);
-                    }
-            }
-        }
-        // toggle the previous group (lag of one group: the row index comes out of the step table and the
-        // row loads depend on it -- the first toggle must not sit at the top of the term)
         if (g0 > 0) {
 #pragma unroll
             for (int u = 0; u < G; u++) {
@@ -131,16 +173,14 @@ __device__ __forceinline__ void pow_term_toggle(const PowParams<C>& p, int row, 
                 if (!REALROW) ci[j] = fma(sg, a.y, ci[j]);
             }
         }
+#pragma unroll 1
+        for (int k = (g0 == 0 ? 1 : 0); k < mmax; k++) {
 #pragma unroll
-        for (int u = 0; u < G; u++)
-            if (g0 + u < M) {
-                if (g0 == 0) {
-                    qr[u] = pr[u];
-                    qi[u] = pi[u];
-                } else {
-                    cmul(qr[u], qi[u], pr[u], pi[u]);
+            for (int u = 0; u < G; u++)
+                if (g0 + u < M) {
+                    if (u == 0 || k < (int)p.cm[g0 + u]) cmul(qr[u], qi[u], cr[g0 + u], ci[g0 + u]);
                 }
-            }
+        }
     }
     // the last group's toggles
     if constexpr (M > 0) {
@@ -167,6 +207,16 @@ __device__ __forceinline__ void pow_term_toggle(const PowParams<C>& p, int row, 
     acc_re = fma(qr[0], f, acc_re);
     acc_im = fma(qi[0], f, acc_im);
     acc_abs = fma(fabs(qr[0]) + fabs(qi[0]), fabs(f), acc_abs);
+}
+
+template <int C, bool GENERAL, bool REALROW>
+__device__ __forceinline__ void pow_term_toggle(const PowParams<C>& p, int row, double sg, double w,
+                                                double (&cr)[C], double (&ci)[C], double& acc_re,
+                                                double& acc_im, double& acc_abs) {
+    if constexpr (GENERAL)
+        pow_term_toggle_general<C, REALROW>(p, row, sg, w, cr, ci, acc_re, acc_im, acc_abs);
+    else
+        pow_term_toggle_single<C, REALROW>(p, row, sg, w, cr, ci, acc_re, acc_im, acc_abs);
 }
 
 template <int C>
@@ -256,7 +306,8 @@ __device__ __noinline__ void grid_reduce_cdd_abs(cdd tot, double ab, double* par
     }
 }
 
-template <int C>
+// GENERAL = false: every column multiplicity is 1 (straight-line term); true: the power form.
+template <int C, bool GENERAL>
 __global__ void __launch_bounds__(kPlainThreads, pow_min_blocks(C))
 glynn_reppow_kernel(const __grid_constant__ PowParams<C> p) {
     const int D = p.D, q = p.q;
@@ -309,9 +360,9 @@ glynn_reppow_kernel(const __grid_constant__ PowParams<C> p) {
             const int row = (int)p.buf.b[p.rowoff + t + 1];
             const double sg = ((p.buf.b[p.flagoff + t + 1] >> P) & 1u) ? -1.0 : 1.0;
             if (row == 1)
-                pow_term_toggle<C, true>(p, p.real_row, sg, w, cr, ci, bs_re, bs_im, bs_abs);
+                pow_term_toggle<C, GENERAL, true>(p, p.real_row, sg, w, cr, ci, bs_re, bs_im, bs_abs);
             else
-                pow_term_toggle<C, false>(p, row, sg, w, cr, ci, bs_re, bs_im, bs_abs);
+                pow_term_toggle<C, GENERAL, false>(p, row, sg, w, cr, ci, bs_re, bs_im, bs_abs);
             if ((t & 7u) == 7u) {  // fold into the double-double accumulator every 8 terms
                 dd_add_d(cacc.re, bs_re);
                 dd_add_d(cacc.im, bs_im);

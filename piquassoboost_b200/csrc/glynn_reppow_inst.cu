@@ -10,8 +10,8 @@
 
 namespace pqb200 {
 
-template <int C>
-static cudaError_t launch_pow_c(const PowLaunchArgs& x) {
+template <int C, bool GENERAL>
+static cudaError_t launch_pow_cg(const PowLaunchArgs& x) {
     static_assert(sizeof(PowParams<C>) <= 32764, "kernel parameter space exceeded");
     constexpr int CS = pow_row_stride(C);
     if (x.C != C || x.R < 2 || x.R - 1 > kPowMaxDigits) return cudaErrorInvalidValue;
@@ -23,7 +23,7 @@ static cudaError_t launch_pow_c(const PowLaunchArgs& x) {
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (occ[dev] == 0) {
         int nb = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, glynn_reppow_kernel<C>, kPlainThreads, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, glynn_reppow_kernel<C, GENERAL>, kPlainThreads, 0);
         if (e != cudaSuccess) return e;
         occ[dev] = nb > 0 ? nb : 1;
     }
@@ -76,8 +76,15 @@ static cudaError_t launch_pow_c(const PowLaunchArgs& x) {
     p.partials = x.partials;
     p.counter = x.counter;
     p.out = x.out;
-    glynn_reppow_kernel<C><<<grid, kPlainThreads, 0, x.stream>>>(p);
+    glynn_reppow_kernel<C, GENERAL><<<grid, kPlainThreads, 0, x.stream>>>(p);
     return cudaGetLastError();
+}
+
+template <int C>
+static cudaError_t launch_pow_c(const PowLaunchArgs& x) {
+    bool general = false;
+    for (int j = 0; j < x.C; j++) general = general || x.cmult[j] != 1;
+    return general ? launch_pow_cg<C, true>(x) : launch_pow_cg<C, false>(x);
 }
 
 template <int LO, int HI>

@@ -2,6 +2,7 @@
 // photon loop of the Clifford-Clifford B sampler, see laplace_sampler.cuh).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 namespace pqb200 {
 
@@ -21,14 +22,21 @@ struct LapLaunch {
     unsigned long long* d_gray_terms;
     const int* d_order;  // [shots] shot index handled by cluster i (NULL = identity)
     int cluster;         // CTAs per shot: 1, 2, 4 or 8
+    int chunks_per_owner;  // low/high digit split: chunks aimed at per term owner (0 = default 8)
     int mode;  // 0: whole shots (fill_r_sample), 1: one pmf layer
 };
 
-// CTAs per shot such that shots x cluster covers the device's CTA slots about `waves` times
+// CTAs per shot: the largest cluster that still fits the device's resident CTA slots in one wave
 inline int lap_cluster_for(size_t shots, int sm_count) {
+    if (const char* f = getenv("PQB200_LAP_CLUSTER")) {  // tuning aid
+        const int v = atoi(f);
+        if (v == 1 || v == 2 || v == 4 || v == 8) return v;
+    }
+    // measured (tools/sampler_sweep.py, profiles/sampler_sweep_r2.log): every CTA of a cluster repeats the
+    // per-step preparation, so splitting only pays while it fills otherwise idle SMs
     const size_t slots = (size_t)sm_count * 3;
     int cs = 1;
-    while (cs < 8 && shots * (size_t)cs < 6 * slots) cs *= 2;
+    while (cs < 8 && shots * (size_t)cs * 2 <= slots) cs *= 2;
     return cs;
 }
 

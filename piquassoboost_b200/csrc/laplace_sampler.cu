@@ -3,6 +3,8 @@
 
 #include "laplace_host.h"
 
+#include <stdlib.h>
+
 namespace pqb200 {
 
 static_assert(kLapMaxPhotons == kLapPhotonsMax, "laplace constants");
@@ -38,9 +40,18 @@ cudaError_t lap_launch(const LapLaunch& l, cudaStream_t stream) {
     a.pmf_out = l.d_pmf;
     a.gray_terms = l.d_gray_terms;
     a.order = l.d_order;
+    a.chunks_per_owner = l.chunks_per_owner > 0 ? l.chunks_per_owner : 8;
+    if (const char* f = getenv("PQB200_LAP_CHUNKS")) {  // tuning aid
+        const int v = atoi(f);
+        if (v >= 1 && v <= 64) a.chunks_per_owner = v;
+    }
     a.mode = l.mode;
     const int cs = (l.cluster == 2 || l.cluster == 4 || l.cluster == 8) ? l.cluster : 1;
     static_assert(kLapMaxCluster == 8, "cluster sizes");
+    if (cs == 1) {  // no cluster: the plain launch
+        laplace_sampler_kernel<<<l.shots, kLapThreads, 0, stream>>>(a);
+        return cudaGetLastError();
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)l.shots * (unsigned)cs, 1, 1);
     cfg.blockDim = dim3(kLapThreads, 1, 1);

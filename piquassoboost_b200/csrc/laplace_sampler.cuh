@@ -57,6 +57,7 @@ struct LapArgs {
     int shots;
     int nmax;                        // row length of ins / rnd
     const int* order;                // [shots] shot handled by cluster i (descending cost), NULL = identity
+    int chunks_per_owner;            // chunks per term owner the low/high digit split aims at
     const int* nphot;                // [shots] photon steps of the shot                    (mode 0)
     const unsigned char* ins;        // [shots][nmax] input mode of the k-th inserted photon (mode 0)
     const double* rnd;               // [shots][nmax] uniform draw of step k                 (mode 0)
@@ -75,7 +76,11 @@ struct LapShared {
     double2 red[kLapThreads / 32][kLapMaxPhotons];
     double2 cred[kLapMaxCluster][kLapMaxPhotons];  // rank 0: the partial addends of every CTA of the cluster
     double2 addend[kLapMaxPhotons];
+    double2 wadd[kLapMaxPhotons];   // weighted addends of the distinct occupied input modes ...
     double p[256];
+    double tot;
+    int nd;                         // ... and how many there are
+    unsigned char wcol[kLapMaxPhotons];
     unsigned long long highW[kLapMaxPhotons];
     unsigned long long nchunks;
     unsigned int lowW[kLapMaxPhotons];
@@ -283,7 +288,7 @@ __device__ __forceinline__ void lap_prepare(LapShared& sh, const LapArgs& a, con
         double total = 1.0;
         for (int d = 0; d < R - 1; d++) total *= (double)sh.radix[d];
         const int G = kLapThreads / lap_lanes(N) * (int)csize;
-        double want = total / (8.0 * G);
+        double want = total / ((double)a.chunks_per_owner * G);
         want = want < 1.0 ? 1.0 : want > (double)kLapMaxLen ? (double)kLapMaxLen : want;
         unsigned int len = 1;
         int q = 0;
@@ -304,32 +309,50 @@ __device__ __forceinline__ void lap_prepare(LapShared& sh, const LapArgs& a, con
     __syncthreads();
     const int R = sh.R, N = sh.N, q = sh.q;
     const unsigned int len = sh.len;
-    // gather (adaptInterferometer, BatchedPermanentCalculator.cpp:412-451); padding columns hold the
-    // constant 1 in the anchor row so that their column sum is 1 for every term
-    for (int e = tid; e < R * kLapMaxPhotons; e += kLapThreads) {
-        const int i = e / kLapMaxPhotons, j = e % kLapMaxPhotons;
-        double2 v = make_double2(i == 0 ? 1.0 : 0.0, 0.0);
-        if (j < N) v = a.U[(size_t)sh.gidx[i] * a.ustride + sh.pidx[j]];
-        sh.A[i][j] = v;
+    // gather (adaptInterferometer, BatchedPermanentCalculator.cpp:412-451): R x N loads from U; the
+    // padding columns (the sweep works on whole groups of NC columns per lane) hold the constant 1 in
+    // the anchor row so that their column sum is 1 for every term
+    for (int e = tid; e < R * N; e += kLapThreads) {
+        const int i = e / N, j = e - i * N;
+        sh.A[i][j] = a.U[(size_t)sh.gidx[i] * a.ustride + sh.pidx[j]];
     }
-    // low-digit step table: changed digit, direction for both high parities, signed binomial weight
+    for (int e = tid; e < R * (kLapMaxPhotons - N); e += kLapThreads) {
+        const int i = e / (kLapMaxPhotons - N), j = N + e - i * (kLapMaxPhotons - N);
+        sh.A[i][j] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);
+    }
+    // low-digit step table: changed digit, direction for both high parities, signed binomial weight.
+    // The counter digits of t come from ONE chain of divisions (least significant digit first); the
+    // changed digit is the lowest non-zero one, and the reflected Gray values for both parities of the
+    // high digits follow from a single pass from the most significant digit down.
     for (unsigned int t = tid; t < len; t += kLapThreads) {
+        unsigned long long pk = 0ull;  // counter digits, 6 bits each (q <= log2(kLapMaxLen) = 9 digits < 41)
+        unsigned int rem = t;
         int ch = 0;
+        bool found = false;
+#pragma unroll 1
         for (int d = 0; d < q; d++) {
-            if ((t / sh.lowW[d]) % sh.radix[d] != 0) { ch = d; break; }
+            const unsigned int rd = sh.radix[d];
+            const unsigned int qq = rem / rd;
+            const unsigned int cd = rem - qq * rd;
+            pk |= (unsigned long long)cd << (6 * d);
+            rem = qq;
+            if (!found && cd != 0) {
+                ch = d;
+                found = true;
+            }
         }
         unsigned int flags = 0;
         double w = 1.0;
-        for (int P = 0; P < 2; P++) {
-            int par = P;
-            for (int d = q - 1; d >= 0; d--) {
-                const int r = sh.radix[d] - 1;
-                const int cnt = (int)((t / sh.lowW[d]) % sh.radix[d]);
-                const int gk = par ? r - cnt : cnt;
-                if (d == ch && par == 0) flags |= 1u << P;
-                par ^= gk & 1;
-                if (P == 0) w *= c_lap_binom[r][gk];
-            }
+        int par0 = 0, par1 = 1;
+#pragma unroll 1
+        for (int d = q - 1; d >= 0; d--) {
+            const int r = sh.radix[d] - 1;
+            const int c = (int)((pk >> (6 * d)) & 63ull);
+            const int g0 = par0 ? r - c : c, g1 = par1 ? r - c : c;
+            if (d == ch) flags = (par0 == 0 ? 1u : 0u) | (par1 == 0 ? 2u : 0u);
+            par0 ^= g0 & 1;
+            par1 ^= g1 & 1;
+            w *= c_lap_binom[r][g0];
         }
         RepStep e;
         e.w = (t & 1u) ? -w : w;
@@ -417,37 +440,84 @@ __global__ void __launch_bounds__(kLapThreads, 3) laplace_sampler_kernel(const L
         // ---- amplitudes and probabilities of the m output modes (samplingHelperFunctions.cpp:308-339):
         //      rank 0 of the cluster holds the complete addends
         if (crank == 0) {
-            const double sc = sh.K > 0 ? ldexp(1.0, -(sh.K - 1)) : 1.0;
-            for (int mm = tid; mm < m; mm += kLapThreads) {
-                double re = 0.0, im = 0.0;
+            // weighted addends of the DISTINCT occupied input modes, compacted (thread 0: N <= 40 entries)
+            if (tid == 0) {
+                const double sc = sh.K > 0 ? ldexp(1.0, -(sh.K - 1)) : 1.0;
+                int nd = 0;
                 for (int j = 0; j < N; j++) {
                     if (!sh.first[j]) continue;
                     const int col = sh.pidx[j];
                     const double cw = (double)sh.cur[col] * sc;
-                    const double wr = cw * sh.addend[j].x, wi = cw * sh.addend[j].y;
-                    const double2 u = a.U[(size_t)mm * a.ustride + col];
-                    re += wr * u.x - wi * u.y;
-                    im += wr * u.y + wi * u.x;
+                    sh.wadd[nd] = make_double2(cw * sh.addend[j].x, cw * sh.addend[j].y);
+                    sh.wcol[nd] = (unsigned char)col;
+                    nd++;
                 }
-                sh.p[mm] = re * re + im * im;
+                sh.nd = nd;
             }
             __syncthreads();
+            // all threads: output mode mm = tid % m, the distinct columns dealt round-robin over the
+            // kLapThreads / m thread groups; partial amplitudes are combined through shared memory
+            const int nd = sh.nd;
+            const int groups = m > 64 ? 1 : (kLapThreads / m > 4 ? 4 : kLapThreads / m);
+            double2* const amp = &sh.cred[0][0];  // [4][64] partial amplitudes; `cred` is free by now
+            static_assert(kLapMaxCluster * kLapMaxPhotons >= 4 * 64, "amplitude scratch aliases cred");
+            if (groups > 1) {
+                const int mm = tid % m, grp = tid / m;
+                double re = 0.0, im = 0.0;
+                if (grp < groups) {
+                    for (int k = grp; k < nd; k += groups) {
+                        const double2 wv = sh.wadd[k];
+                        const double2 u = a.U[(size_t)mm * a.ustride + sh.wcol[k]];
+                        re += wv.x * u.x - wv.y * u.y;
+                        im += wv.x * u.y + wv.y * u.x;
+                    }
+                    amp[grp * 64 + mm] = make_double2(re, im);
+                }
+                __syncthreads();
+                if (tid < m) {
+                    re = 0.0;
+                    im = 0.0;
+                    for (int g2 = 0; g2 < groups; g2++) {
+                        re += amp[g2 * 64 + tid].x;
+                        im += amp[g2 * 64 + tid].y;
+                    }
+                    sh.p[tid] = re * re + im * im;
+                }
+            } else {
+                for (int mm = tid; mm < m; mm += kLapThreads) {
+                    double re = 0.0, im = 0.0;
+                    for (int k = 0; k < nd; k++) {
+                        const double2 wv = sh.wadd[k];
+                        const double2 u = a.U[(size_t)mm * a.ustride + sh.wcol[k]];
+                        re += wv.x * u.x - wv.y * u.y;
+                        im += wv.x * u.y + wv.y * u.x;
+                    }
+                    sh.p[mm] = re * re + im * im;
+                }
+            }
+            __syncthreads();
+            // probability_sum (sequential, as the reference forms it) and the normalised layer
             if (tid == 0) {
                 double tot = 0.0;
                 for (int i = 0; i < m; i++) tot += sh.p[i];
-                if (a.mode == 0) {
+                sh.tot = tot;
+            }
+            __syncthreads();
+            if (a.mode == 0) {
+                const double tot = sh.tot;
+                for (int i = tid; i < m; i += kLapThreads) sh.p[i] = sh.p[i] / tot;
+                __syncthreads();
+                if (tid == 0) {
                     // sample_from_pmf (samplingHelperFunctions.cpp:350-374): first index whose cumulative
                     // normalised probability reaches the draw, 0 if none does
                     const double r = a.rnd[(size_t)s * a.nmax + k];
                     int chosen = 0;
                     double acc = 0.0;
                     for (int i = 0; i < m; i++) {
-                        acc += sh.p[i] / tot;
+                        acc += sh.p[i];
                         if (acc >= r) { chosen = i; break; }
                     }
                     for (unsigned int r2 = 0; r2 < csize; r2++) cluster.map_shared_rank(&sh, r2)->chosen = chosen;
-                } else {
-                    sh.p[255] = tot;  // m <= 255: slot 255 is free
                 }
             }
         }
@@ -461,7 +531,7 @@ __global__ void __launch_bounds__(kLapThreads, 3) laplace_sampler_kernel(const L
         if (a.mode == 0) {
             for (int i = tid; i < m; i += kLapThreads) a.samples_out[(size_t)s * m + i] = (long long)sh.sample[i];
         } else {
-            const double tot = sh.p[255];
+            const double tot = sh.tot;
             for (int i = tid; i < m; i += kLapThreads) a.pmf_out[(size_t)s * m + i] = sh.p[i] / tot;
         }
     }

@@ -841,10 +841,11 @@ int pqb200_permanent_repeated_dd(const double* a, size_t rows, size_t cols, size
 // A-posteriori rounding-error bound of the fast repeated kernel: eps * (photons + 8) * sum|term| /
 // |sum|.  Every term is a product of `photons` FP64 factors, each carrying a few roundings of its
 // column sum; the bound treats them as adding up linearly (worst case), so the true error is well
-// below it (tests/test_repeated_gpu.py records both).  Above kRepeatedDDThreshold the call is
+// below it: measured bound / error = 35 ... 800 (profiles/repeated_bound_calibration_r2.json), so a
+// threshold of 2e-9 keeps the fast kernel's error below 6e-11.  Above kRepeatedDDThreshold the call is
 // re-evaluated in double-double arithmetic -- what the reference does up front by size / request
 // (BBFGPermanentCalculatorRepeated.cpp:105-141 use_extended / use_inf) is decided here by measurement.
-constexpr double kRepeatedDDThreshold = 2.0e-8;
+constexpr double kRepeatedDDThreshold = 2.0e-9;
 thread_local double g_last_bound = 0.0;
 thread_local int g_last_dd = 0;
 

@@ -100,8 +100,12 @@ def permanent_distributed(a, group=None, device=None, shard_fn=None):
         dev = torch.device("cuda", device)
         partial = torch.zeros(4, dtype=torch.float64, device=dev)
         gathered = torch.zeros(4 * world, dtype=torch.float64, device=dev)
-        gpu_shard_fn(a, rank, world, device, d_out=partial.data_ptr(),
-                     stream=torch.cuda.current_stream(dev).cuda_stream or None)
+        # the kernel is enqueued on torch's CURRENT stream of the device -- the stream the all-gather
+        # below is ordered against.  Handle 0 is the legacy default stream: cudaStreamLegacy (0x1) names
+        # it explicitly (a NULL stream argument also means "the caller's legacy default stream" when
+        # d_out is given, include/pqb200.h).
+        handle = torch.cuda.current_stream(dev).cuda_stream
+        gpu_shard_fn(a, rank, world, device, d_out=partial.data_ptr(), stream=handle or 0x1)
     else:
         dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
         partial = torch.as_tensor(np.asarray(shard_fn(a, rank, world), dtype=np.float64)).to(dev)

@@ -1,5 +1,6 @@
 """Kernel times of a few repeated-row permanents of different N (tuning aid; PQB200_LIB selects the build)."""
 import os, sys
+os.environ.setdefault("PQB200_NO_DD_FALLBACK", "1")   # time the fast kernel only
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from scipy.stats import unitary_group
@@ -26,3 +27,13 @@ run("N20-10x2", U, inp, out)
 inp = np.zeros(60, dtype=np.int64); inp[:36] = 1
 out = np.zeros(60, dtype=np.int64); out[:18] = 2
 run("N36-18x2", U, inp, out)
+# both sides repeated: the power form keeps C < N column sums
+inp = np.zeros(60, dtype=np.int64); inp[:10] = 3
+out = np.zeros(60, dtype=np.int64); out[:15] = 2
+run("N30-10x3-into-15x2", U, inp, out)
+inp = np.zeros(60, dtype=np.int64); inp[:15] = 2
+out = np.zeros(60, dtype=np.int64); out[20:35] = 2
+run("N30-15x2-into-15x2", U, inp, out)
+inp = np.zeros(60, dtype=np.int64); inp[:10] = 6
+out = np.zeros(60, dtype=np.int64); out[:10] = [7, 5, 6, 6, 8, 4, 6, 6, 5, 7]
+run("N60-10x6-into-10", U, inp, out)

@@ -1,0 +1,40 @@
+"""Kernel / call time of the C5-shaped B sampler (20 photons, 40 modes) for a few shot counts under the
+tuning knobs PQB200_LAP_CLUSTER / PQB200_LAP_WAVES / PQB200_LAP_CHUNKS (one child process per setting: the
+knobs are read from the environment)."""
+import json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CHILD = r"""
+import os, sys, time, json
+sys.path.insert(0, %r)
+import numpy as np
+from scipy.stats import unitary_group
+import piquassoboost_b200 as pqb
+U = np.ascontiguousarray(unitary_group.rvs(40, random_state=5))
+state = np.array([1] * 20 + [0] * 20, dtype=np.int64)
+shots = int(sys.argv[1]); nd = int(sys.argv[2])
+sim = pqb.GeneralizedCliffordsBSimulationStrategy(U, seed=5, ndev=nd)
+sim.simulate(state, shots)
+best = (1e9, None)
+for r in range(3):
+    sim.seed(5)
+    t = time.perf_counter(); res = sim.simulate(state, shots); dt = time.perf_counter() - t
+    st = pqb.last_stats()
+    if dt < best[0]: best = (dt, st)
+print(json.dumps({"shots": shots, "ndev": best[1]["ndev"], "call_ms": best[0] * 1e3, "kernel_ms": best[1]["kernel_ms"],
+                  "launches": best[1]["launches"], "checksum": int(np.array(res).astype(np.int64).dot(np.arange(40)).sum())}))
+""" % ROOT
+ndevs = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "1").split(",")]
+for shots in (125, 1000, 20000):
+    for nd in ndevs:
+        for cl in ("auto", "1", "2", "4", "8"):
+            for wv in ("auto", "1", "4"):
+                for ch in ("8", "4"):
+                    if (wv != "auto" or ch != "8") and cl not in ("auto", "1"):
+                        continue
+                    env = dict(os.environ)
+                    if cl != "auto": env["PQB200_LAP_CLUSTER"] = cl
+                    if wv != "auto": env["PQB200_LAP_WAVES"] = wv
+                    env["PQB200_LAP_CHUNKS"] = ch
+                    r = subprocess.run([sys.executable, "-c", CHILD, str(shots), str(nd)], capture_output=True, text=True, env=env)
+                    line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:]
+                    print(f"cluster={cl} waves={wv} chunks={ch} {line}", flush=True)
