@@ -284,7 +284,7 @@ class RepeatedPermanentCalculator(ChinHuhPermanentCalculator_wrapper):
             elif any(not isinstance(item, np.ndarray) for item in input_state):
                 if all(np.isscalar(item) for item in input_state):
                     input_state = np.array(input_state, dtype=np.int64)
-                elif not all(isinstance(item, list) for item in input_state):
+                else:
                     raise Exception('The input state should be a numpy array, or a list of numpy arrays')
         if not isinstance(output_state, np.ndarray):
             if not isinstance(output_state, list):
@@ -292,7 +292,7 @@ class RepeatedPermanentCalculator(ChinHuhPermanentCalculator_wrapper):
             elif any(not isinstance(item, np.ndarray) for item in output_state):
                 if all(np.isscalar(item) for item in output_state):
                     output_state = np.array(output_state, dtype=np.int64)
-                elif not all(isinstance(item, list) for item in output_state):
+                else:
                     raise Exception('The output state should be a numpy array, or a list of numpy arrays')
         super().__init__(lib=lib, matrix=matrix, input_state=input_state, output_state=output_state)
 

@@ -22,9 +22,25 @@ struct LapLaunch {
     unsigned long long* d_gray_terms;
     const int* d_order;  // [shots] shot index handled by cluster i (NULL = identity)
     int cluster;         // CTAs per shot: 1, 2, 4 or 8
-    int chunks_per_owner;  // low/high digit split: chunks aimed at per term owner (0 = default 8)
+    int chunks_per_owner;  // low/high digit split: chunks aimed at per term owner (0 = default 4, measured)
+    unsigned long long* d_prof;  // PQB_LAP_PROFILE builds only
+    int step_begin, step_end;    // mode 0: photon steps [step_begin, step_end) of every shot (0, nmax = all)
+    unsigned char* d_state;      // mode 0: [shots][2][m] hand-over state between launches over step ranges
+    float* d_cost;               // mode 0: [shots] cost estimate written at the hand-over
     int mode;  // 0: whole shots (fill_r_sample), 1: one pmf layer
 };
+
+// Photon steps left to the second, cost-ordered launch of a wave (0: a single launch).
+inline int lap_tail_steps(size_t shots, int nmax, int sm_count) {
+    int tail = 3;
+    const size_t slots = (size_t)sm_count * 3;
+    if (nmax < 10 || shots <= slots || shots > 6 * slots) tail = 0;  // everything resident at once / enough shots to balance
+    if (const char* f = getenv("PQB200_LAP_TAIL")) {  // tuning aid
+        const int v = atoi(f);
+        if (v >= 0 && v < nmax) tail = v;
+    }
+    return tail;
+}
 
 // CTAs per shot: the largest cluster that still fits the device's resident CTA slots in one wave
 inline int lap_cluster_for(size_t shots, int sm_count) {

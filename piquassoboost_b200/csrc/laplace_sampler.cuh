@@ -19,9 +19,14 @@
 //     launch: insertion order and the uniform draws of the shot are pre-resolved on the host from the
 //     reference's std::mt19937 stream (they do not depend on the pmf values), so there is no host round
 //     trip between steps.  The CTAs of a cluster split the chunks of every Gray sweep and combine their
-//     partial addends through distributed shared memory in a fixed order; the host picks the cluster
-//     size so that shots x cluster covers the GPU several times (a 125-shot shard of an 8-GPU run would
-//     otherwise occupy a quarter of the SMs) and hands out the shots in descending photon count.
+//     partial addends through distributed shared memory in a fixed order.  Every CTA of a cluster repeats
+//     the step's preparation, so the host only uses clusters to fill otherwise idle SMs (a 125-shot shard
+//     of an 8-GPU run would occupy a quarter of them).
+//   * A shot's cost is set by the collisions in its sample, which nobody knows in advance, and a wave of
+//     1000 shots on 444 resident CTAs is only 2.25 shots per CTA: handed out blindly, the last CTAs run
+//     alone for a third of the launch.  So a wave is TWO launches: all photon steps but the last three,
+//     then -- with the shots re-ordered by the size of the Gray space they have reached, longest first --
+//     the last three steps, which hold 7/8 of the arithmetic (each step costs twice the one before).
 //   * Per step the CTA builds the job in shared memory (rows / radices from `sample`, physically
 //     repeated columns from `cur`, gather of the sub-matrix from U = adaptInterferometer), the
 //     low-digit step table and the two base vectors -- same low/high digit split of the reflected
@@ -50,6 +55,23 @@ constexpr int kLapMaxCluster = 8;   // CTAs that share one shot (portable cluste
 
 static __constant__ double c_lap_binom[kLapBinomDim][kLapBinomDim];
 
+// PQB_LAP_PROFILE (tuning builds only): thread 0 of every CTA accumulates the cycles between phase
+// boundaries into LapArgs::prof[phase] (tools/sampler_phases.py prints the shares)
+#ifdef PQB_LAP_PROFILE
+#define LAP_TICK(ph)                                                                   \
+    do {                                                                               \
+        if (threadIdx.x == 0 && a.prof) {                                              \
+            const long long now__ = clock64();                                         \
+            atomicAdd(a.prof + (ph), (unsigned long long)(now__ - lap_t0__));          \
+            lap_t0__ = now__;                                                          \
+        }                                                                              \
+    } while (0)
+#define LAP_TICK_DECL long long lap_t0__ = clock64()
+#else
+#define LAP_TICK(ph) do {} while (0)
+#define LAP_TICK_DECL do {} while (0)
+#endif
+
 struct LapArgs {
     const double2* U;  // m x m interferometer, row stride `ustride` complex elements
     int ustride;
@@ -58,6 +80,15 @@ struct LapArgs {
     int nmax;                        // row length of ins / rnd
     const int* order;                // [shots] shot handled by cluster i (descending cost), NULL = identity
     int chunks_per_owner;            // chunks per term owner the low/high digit split aims at
+    unsigned long long* prof;        // PQB_LAP_PROFILE builds: [16] cycle counters per phase (else unused)
+    // mode 0 may be run as several launches over consecutive ranges of photon steps (the light early
+    // steps one CTA per shot, the heavy last steps split over a cluster): this launch does steps
+    // [step_begin, step_end) of every shot; `state` ([shots][2][m] bytes: sample, cur) carries a shot
+    // from one launch to the next
+    int step_begin, step_end;
+    unsigned char* state;
+    float* cost;                     // [shots] Gray terms of the last step a handed-over shot has done: the
+                                     // host orders the next launch by it (longest first)
     const int* nphot;                // [shots] photon steps of the shot                    (mode 0)
     const unsigned char* ins;        // [shots][nmax] input mode of the k-th inserted photon (mode 0)
     const double* rnd;               // [shots][nmax] uniform draw of step k                 (mode 0)
@@ -76,11 +107,8 @@ struct LapShared {
     double2 red[kLapThreads / 32][kLapMaxPhotons];
     double2 cred[kLapMaxCluster][kLapMaxPhotons];  // rank 0: the partial addends of every CTA of the cluster
     double2 addend[kLapMaxPhotons];
-    double2 wadd[kLapMaxPhotons];   // weighted addends of the distinct occupied input modes ...
     double p[256];
     double tot;
-    int nd;                         // ... and how many there are
-    unsigned char wcol[kLapMaxPhotons];
     unsigned long long highW[kLapMaxPhotons];
     unsigned long long nchunks;
     unsigned int lowW[kLapMaxPhotons];
@@ -248,65 +276,119 @@ __device__ __noinline__ void lap_sweep(LapShared& sh, const unsigned int crank, 
 
 // Build the step's job in shared memory from sh.sample / sh.cur (thread 0), then gather and tabulate
 // (all threads).  Returns with everything lap_sweep needs in place.
-__device__ __forceinline__ void lap_prepare(LapShared& sh, const LapArgs& a, const unsigned int csize) {
+#ifdef PQB_LAP_PROFILE
+#define LAP_T0_PARAM , long long& lap_t0__
+#define LAP_T0_ARG , lap_t0__
+#else
+#define LAP_T0_PARAM
+#define LAP_T0_ARG
+#endif
+__device__ __forceinline__ void lap_prepare(LapShared& sh, const LapArgs& a, const unsigned int csize LAP_T0_PARAM) {
     const int tid = threadIdx.x, m = a.m;
-    if (tid == 0) {
-        // rows: occupied output modes; the anchor takes one copy of the first minimum-multiplicity
-        // row (BBFGPermanentCalculatorRepeated.hpp:78-94)
-        int K = 0, amin = -1, mn = 1 << 30;
-        for (int i = 0; i < m; i++) {
-            const int v = sh.sample[i];
-            if (v > 0) {
-                K += v;
-                if (v < mn) { mn = v; amin = i; }
+    if (tid < 32) {
+        // Warp 0 builds the job cooperatively: lane L owns the modes [8L, 8L+8) (m <= 255), positions in
+        // the row / column lists come from warp prefix sums, so the lists keep the reference's mode order.
+        const unsigned int FULL = 0xffffffffu;
+        const int lo = 8 * tid;
+        // rows: occupied output modes; the anchor takes one copy of the FIRST minimum-multiplicity row
+        // (BBFGPermanentCalculatorRepeated.hpp:78-94): minimise (multiplicity, index)
+        int K = 0;
+        unsigned int key = 0xffffffffu;
+        unsigned char smp[8], cu[8];
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const int i = lo + b;
+            smp[b] = i < m ? sh.sample[i] : 0;
+            cu[b] = i < m ? sh.cur[i] : 0;
+            K += smp[b];
+            if (smp[b] > 0) {
+                const unsigned int k2 = ((unsigned int)smp[b] << 8) | (unsigned int)i;
+                key = k2 < key ? k2 : key;
             }
         }
-        int R = 0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            K += __shfl_xor_sync(FULL, K, off);
+            const unsigned int o = __shfl_xor_sync(FULL, key, off);
+            key = o < key ? o : key;
+        }
+        const int amin = key == 0xffffffffu ? -1 : (int)(key & 0xffu);
+        int nrow = 0, ncol = 0;
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            nrow += ((int)smp[b] - (lo + b == amin ? 1 : 0)) > 0 ? 1 : 0;
+            ncol += cu[b];
+        }
+        int prow = nrow, pcol = ncol;  // inclusive prefix sums over the lanes
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int a1 = __shfl_up_sync(FULL, prow, off), a2 = __shfl_up_sync(FULL, pcol, off);
+            if (tid >= off) {
+                prow += a1;
+                pcol += a2;
+            }
+        }
+        const int R = amin >= 0 ? 1 + __shfl_sync(FULL, prow, 31) : 0;
+        int Ntot = __shfl_sync(FULL, pcol, 31);
+        Ntot = Ntot > kLapMaxPhotons ? kLapMaxPhotons : Ntot;
         if (amin >= 0) {
-            sh.gidx[R++] = (unsigned char)amin;
-            for (int i = 0; i < m; i++) {
-                const int ml = (int)sh.sample[i] - (i == amin ? 1 : 0);
+            if (tid == 0) sh.gidx[0] = (unsigned char)amin;
+            int pos = 1 + prow - nrow;
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                const int ml = (int)smp[b] - (lo + b == amin ? 1 : 0);
                 if (ml > 0) {
-                    sh.radix[R - 1] = (unsigned char)(ml + 1);
-                    sh.gidx[R++] = (unsigned char)i;
+                    sh.radix[pos - 1] = (unsigned char)(ml + 1);
+                    sh.gidx[pos] = (unsigned char)(lo + b);
+                    pos++;
                 }
             }
         }
-        // columns: occupied input modes, physically repeated
-        int N = 0;
-        for (int i = 0; i < m; i++)
-            for (int rep = 0; rep < (int)sh.cur[i] && N < kLapMaxPhotons; rep++) {
-                sh.pidx[N] = (unsigned char)i;
-                sh.first[N] = rep == 0;
-                N++;
-            }
-        sh.R = R;
-        sh.N = N;
-        sh.K = K;
-        // low / high digit split: chunks of at most kLapMaxLen steps, >= 8 chunks per term owner of the
-        // cluster (the last round of chunks is partly idle: at most 1/8 of the sweep)
+        {   // columns: occupied input modes, physically repeated
+            int pos = pcol - ncol;
+#pragma unroll
+            for (int b = 0; b < 8; b++)
+                for (int rep = 0; rep < (int)cu[b] && pos < kLapMaxPhotons; rep++) {
+                    sh.pidx[pos] = (unsigned char)(lo + b);
+                    sh.first[pos] = rep == 0;
+                    pos++;
+                }
+        }
+        __syncwarp();
+        // total Gray terms = prod radix (at most 40 digits: two per lane)
         double total = 1.0;
-        for (int d = 0; d < R - 1; d++) total *= (double)sh.radix[d];
-        const int G = kLapThreads / lap_lanes(N) * (int)csize;
-        double want = total / ((double)a.chunks_per_owner * G);
-        want = want < 1.0 ? 1.0 : want > (double)kLapMaxLen ? (double)kLapMaxLen : want;
-        unsigned int len = 1;
-        int q = 0;
-        while (q < R - 1 && (double)len * sh.radix[q] <= want) {
-            sh.lowW[q] = len;
-            len *= sh.radix[q];
-            q++;
+        if (tid < R - 1) total *= (double)sh.radix[tid];
+        if (tid + 32 < R - 1) total *= (double)sh.radix[tid + 32];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) total *= __shfl_xor_sync(FULL, total, off);
+        if (tid == 0) {
+            sh.R = R;
+            sh.N = Ntot;
+            sh.K = K;
+            // low / high digit split: chunks of at most kLapMaxLen steps, about chunks_per_owner chunks per
+            // term owner of the cluster (the last round of chunks is partly idle)
+            const int G = kLapThreads / lap_lanes(Ntot) * (int)csize;
+            double want = total / ((double)a.chunks_per_owner * G);
+            want = want < 1.0 ? 1.0 : want > (double)kLapMaxLen ? (double)kLapMaxLen : want;
+            unsigned int len = 1;
+            int q = 0;
+            while (q < R - 1 && (double)len * sh.radix[q] <= want) {
+                sh.lowW[q] = len;
+                len *= sh.radix[q];
+                q++;
+            }
+            unsigned long long nch = 1;
+            for (int d = q; d < R - 1; d++) {
+                sh.highW[d] = nch;
+                nch *= sh.radix[d];
+            }
+            sh.q = q;
+            sh.len = len;
+            sh.nchunks = nch;
         }
-        unsigned long long nch = 1;
-        for (int d = q; d < R - 1; d++) {
-            sh.highW[d] = nch;
-            nch *= sh.radix[d];
-        }
-        sh.q = q;
-        sh.len = len;
-        sh.nchunks = nch;
     }
     __syncthreads();
+    LAP_TICK(0);  // job construction (warp 0)
     const int R = sh.R, N = sh.N, q = sh.q;
     const unsigned int len = sh.len;
     // gather (adaptInterferometer, BatchedPermanentCalculator.cpp:412-451): R x N loads from U; the
@@ -320,6 +402,10 @@ __device__ __forceinline__ void lap_prepare(LapShared& sh, const LapArgs& a, con
         const int i = e / (kLapMaxPhotons - N), j = N + e - i * (kLapMaxPhotons - N);
         sh.A[i][j] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);
     }
+#ifdef PQB_LAP_PROFILE
+    __syncthreads();
+#endif
+    LAP_TICK(1);  // gather
     // low-digit step table: changed digit, direction for both high parities, signed binomial weight.
     // The counter digits of t come from ONE chain of divisions (least significant digit first); the
     // changed digit is the lowest non-zero one, and the reflected Gray values for both parities of the
@@ -361,6 +447,7 @@ __device__ __forceinline__ void lap_prepare(LapShared& sh, const LapArgs& a, con
         sh.table[t] = e;
     }
     __syncthreads();
+    LAP_TICK(2);  // step table
     // base vectors: anchor + low rows at their initial Gray value, for both high parities
     for (int e = tid; e < 2 * kLapMaxPhotons; e += kLapThreads) {
         const int P = e / kLapMaxPhotons, j = e % kLapMaxPhotons;
@@ -389,9 +476,22 @@ __global__ void __launch_bounds__(kLapThreads, 3) laplace_sampler_kernel(const L
     const int slot = (int)(blockIdx.x / csize);
     const int s = a.order ? a.order[slot] : slot;
     int steps;
+    LAP_TICK_DECL;
+    int k_first = 0;
     if (a.mode == 0) {
-        for (int i = tid; i < m; i += kLapThreads) sh.sample[i] = sh.cur[i] = 0;
-        steps = a.nphot[s];
+        const int np = a.nphot[s];
+        k_first = a.step_begin < np ? a.step_begin : np;
+        steps = a.step_end < np ? a.step_end : np;
+        if (k_first >= steps && a.step_begin > 0) return;  // the shot was finished by an earlier launch (uniform per cluster)
+        if (k_first == 0) {
+            for (int i = tid; i < m; i += kLapThreads) sh.sample[i] = sh.cur[i] = 0;
+        } else {
+            const unsigned char* st = a.state + (size_t)s * 2 * m;
+            for (int i = tid; i < m; i += kLapThreads) {
+                sh.sample[i] = st[i];
+                sh.cur[i] = st[m + i];
+            }
+        }
     } else {
         for (int i = tid; i < m; i += kLapThreads) {
             sh.sample[i] = a.sample_in[(size_t)s * m + i];
@@ -402,13 +502,14 @@ __global__ void __launch_bounds__(kLapThreads, 3) laplace_sampler_kernel(const L
     __syncthreads();
     // every CTA of the cluster keeps its own copy of the shot's state (sample, cur) and prepares each
     // step redundantly; only the Gray sweep is split
-    for (int k = 0; k < steps; k++) {
+    for (int k = k_first; k < steps; k++) {
         if (a.mode == 0) {
             // update_input_by_single_photon (samplingHelperFunctions.cpp:377-406), order pre-resolved
             if (tid == 0) sh.cur[a.ins[(size_t)s * a.nmax + k]]++;
             __syncthreads();
         }
-        lap_prepare(sh, a, csize);
+        lap_prepare(sh, a, csize LAP_T0_ARG);
+        LAP_TICK(3);  // base vectors
         const int N = sh.N;
         if (tid == 0 && crank == 0 && sh.R > 0) atomicAdd(a.gray_terms, (unsigned long long)sh.len * sh.nchunks);
         if (sh.R == 0) {
@@ -437,27 +538,14 @@ __global__ void __launch_bounds__(kLapThreads, 3) laplace_sampler_kernel(const L
                 default: lap_sweep<10, 4>(sh, crank, csize); break;
             }
         }
+        LAP_TICK(4 + (sh.K < 8 ? 0 : sh.K < 12 ? 1 : sh.K < 16 ? 2 : 3));  // sweep, by photons placed
         // ---- amplitudes and probabilities of the m output modes (samplingHelperFunctions.cpp:308-339):
         //      rank 0 of the cluster holds the complete addends
         if (crank == 0) {
-            // weighted addends of the DISTINCT occupied input modes, compacted (thread 0: N <= 40 entries)
-            if (tid == 0) {
-                const double sc = sh.K > 0 ? ldexp(1.0, -(sh.K - 1)) : 1.0;
-                int nd = 0;
-                for (int j = 0; j < N; j++) {
-                    if (!sh.first[j]) continue;
-                    const int col = sh.pidx[j];
-                    const double cw = (double)sh.cur[col] * sc;
-                    sh.wadd[nd] = make_double2(cw * sh.addend[j].x, cw * sh.addend[j].y);
-                    sh.wcol[nd] = (unsigned char)col;
-                    nd++;
-                }
-                sh.nd = nd;
-            }
-            __syncthreads();
-            // all threads: output mode mm = tid % m, the distinct columns dealt round-robin over the
-            // kLapThreads / m thread groups; partial amplitudes are combined through shared memory
-            const int nd = sh.nd;
+            // All threads: output mode mm = tid % m, the occupied input modes dealt round-robin over the
+            // kLapThreads / m thread groups (fixed trip count, predicated: the loads of U are independent and
+            // issue back to back); partial amplitudes are combined through shared memory.
+            const double sc = sh.K > 0 ? ldexp(1.0, -(sh.K - 1)) : 1.0;
             const int groups = m > 64 ? 1 : (kLapThreads / m > 4 ? 4 : kLapThreads / m);
             double2* const amp = &sh.cred[0][0];  // [4][64] partial amplitudes; `cred` is free by now
             static_assert(kLapMaxCluster * kLapMaxPhotons >= 4 * 64, "amplitude scratch aliases cred");
@@ -465,11 +553,18 @@ __global__ void __launch_bounds__(kLapThreads, 3) laplace_sampler_kernel(const L
                 const int mm = tid % m, grp = tid / m;
                 double re = 0.0, im = 0.0;
                 if (grp < groups) {
-                    for (int k = grp; k < nd; k += groups) {
-                        const double2 wv = sh.wadd[k];
-                        const double2 u = a.U[(size_t)mm * a.ustride + sh.wcol[k]];
-                        re += wv.x * u.x - wv.y * u.y;
-                        im += wv.x * u.y + wv.y * u.x;
+#pragma unroll
+                    for (int it = 0; it < (kLapMaxPhotons + 1) / 2; it++) {  // groups >= 2: at most 20 columns per group
+                        const int j = grp + it * groups;
+                        if (j < N && sh.first[j]) {
+                            const int col = sh.pidx[j];
+                            const double cw = (double)sh.cur[col] * sc;
+                            const double2 ad = sh.addend[j];
+                            const double2 u = a.U[(size_t)mm * a.ustride + col];
+                            const double wr = cw * ad.x, wi = cw * ad.y;
+                            re += wr * u.x - wi * u.y;
+                            im += wr * u.y + wi * u.x;
+                        }
                     }
                     amp[grp * 64 + mm] = make_double2(re, im);
                 }
@@ -486,38 +581,64 @@ __global__ void __launch_bounds__(kLapThreads, 3) laplace_sampler_kernel(const L
             } else {
                 for (int mm = tid; mm < m; mm += kLapThreads) {
                     double re = 0.0, im = 0.0;
-                    for (int k = 0; k < nd; k++) {
-                        const double2 wv = sh.wadd[k];
-                        const double2 u = a.U[(size_t)mm * a.ustride + sh.wcol[k]];
-                        re += wv.x * u.x - wv.y * u.y;
-                        im += wv.x * u.y + wv.y * u.x;
+                    for (int j = 0; j < N; j++) {
+                        if (!sh.first[j]) continue;
+                        const int col = sh.pidx[j];
+                        const double cw = (double)sh.cur[col] * sc;
+                        const double wr = cw * sh.addend[j].x, wi = cw * sh.addend[j].y;
+                        const double2 u = a.U[(size_t)mm * a.ustride + col];
+                        re += wr * u.x - wi * u.y;
+                        im += wr * u.y + wi * u.x;
                     }
                     sh.p[mm] = re * re + im * im;
                 }
             }
             __syncthreads();
-            // probability_sum (sequential, as the reference forms it) and the normalised layer
-            if (tid == 0) {
-                double tot = 0.0;
-                for (int i = 0; i < m; i++) tot += sh.p[i];
-                sh.tot = tot;
-            }
-            __syncthreads();
-            if (a.mode == 0) {
-                const double tot = sh.tot;
-                for (int i = tid; i < m; i += kLapThreads) sh.p[i] = sh.p[i] / tot;
-                __syncthreads();
-                if (tid == 0) {
-                    // sample_from_pmf (samplingHelperFunctions.cpp:350-374): first index whose cumulative
-                    // normalised probability reaches the draw, 0 if none does
-                    const double r = a.rnd[(size_t)s * a.nmax + k];
-                    int chosen = 0;
-                    double acc = 0.0;
-                    for (int i = 0; i < m; i++) {
-                        acc += sh.p[i];
-                        if (acc >= r) { chosen = i; break; }
+            // Warp 0: probability_sum, the normalised layer and the draw (sample_from_pmf,
+            // samplingHelperFunctions.cpp:350-374: the first index whose cumulative normalised probability
+            // reaches the draw, 0 if none does).  Lane L owns the modes [8L, 8L+8); the cumulative sums come
+            // from a warp prefix scan, i.e. in another association order than the reference's running sum
+            // (differences of an ulp, far below the kernel's own rounding).
+            if (tid < 32) {
+                const unsigned int FULL = 0xffffffffu;
+                double pv[8], part = 0.0;
+#pragma unroll
+                for (int b = 0; b < 8; b++) {
+                    const int i = 8 * tid + b;
+                    pv[b] = i < m ? sh.p[i] : 0.0;
+                    part += pv[b];
+                }
+                double tot = part;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(FULL, tot, off);
+                if (a.mode == 0) {
+                    double run = 0.0;
+#pragma unroll
+                    for (int b = 0; b < 8; b++) {
+                        pv[b] = pv[b] / tot;  // the normalised layer
+                        run += pv[b];
                     }
-                    for (unsigned int r2 = 0; r2 < csize; r2++) cluster.map_shared_rank(&sh, r2)->chosen = chosen;
+                    double incl = run;  // inclusive prefix of the lanes' sums
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const double o = __shfl_up_sync(FULL, incl, off);
+                        if (tid >= off) incl += o;
+                    }
+                    const double r = a.rnd[(size_t)s * a.nmax + k];
+                    double acc = incl - run;
+                    int hit = -1;
+#pragma unroll
+                    for (int b = 0; b < 8; b++) {
+                        acc += pv[b];
+                        if (hit < 0 && 8 * tid + b < m && acc >= r) hit = 8 * tid + b;
+                    }
+                    const unsigned int any = __ballot_sync(FULL, hit >= 0);
+                    int chosen = 0;
+                    if (any) chosen = __shfl_sync(FULL, hit, __ffs(any) - 1);
+                    if (tid == 0)
+                        for (unsigned int r2 = 0; r2 < csize; r2++) cluster.map_shared_rank(&sh, r2)->chosen = chosen;
+                } else if (tid == 0) {
+                    sh.tot = tot;
                 }
             }
         }
@@ -526,10 +647,20 @@ __global__ void __launch_bounds__(kLapThreads, 3) laplace_sampler_kernel(const L
             if (tid == 0) sh.sample[sh.chosen]++;
             __syncthreads();
         }
+        LAP_TICK(8);  // amplitudes, pmf, draw
     }
     if (crank == 0) {
         if (a.mode == 0) {
-            for (int i = tid; i < m; i += kLapThreads) a.samples_out[(size_t)s * m + i] = (long long)sh.sample[i];
+            if (steps >= a.nphot[s]) {
+                for (int i = tid; i < m; i += kLapThreads) a.samples_out[(size_t)s * m + i] = (long long)sh.sample[i];
+            } else {  // hand the shot over to the next launch
+                if (tid == 0) a.cost[s] = sh.R > 0 ? (float)sh.len * (float)sh.nchunks : 1.0f;
+                unsigned char* st = a.state + (size_t)s * 2 * m;
+                for (int i = tid; i < m; i += kLapThreads) {
+                    st[i] = sh.sample[i];
+                    st[m + i] = sh.cur[i];
+                }
+            }
         } else {
             const double tot = sh.tot;
             for (int i = tid; i < m; i += kLapThreads) a.pmf_out[(size_t)s * m + i] = sh.p[i] / tot;

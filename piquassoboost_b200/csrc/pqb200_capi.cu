@@ -100,6 +100,7 @@ struct DeviceCtx {
     double* d_out = nullptr;  // 8 doubles
     double* h_out = nullptr;  // pinned, 8 doubles
     cudaEvent_t e0 = nullptr, e1 = nullptr;
+    std::vector<cudaEvent_t> evs;  // extra timing events (calls that time several separate launches)
     // Recorded behind work that an asynchronous entry point (pqb200_permanent_shard with d_out,
     // pqb200_permanent_nccl_async) left in flight on a CALLER's stream: every later use of the slot's
     // workspaces is ordered behind it with cudaStreamWaitEvent.
@@ -578,6 +579,8 @@ void pqb200_shutdown(void) {
             cudaEventDestroy(c.e0);
             cudaEventDestroy(c.e1);
             cudaEventDestroy(c.busy);
+            for (cudaEvent_t e : c.evs) cudaEventDestroy(e);
+            c.evs.clear();
             cudaStreamDestroy(c.stream);
             c.partials = nullptr; c.counter = nullptr; c.d_out = nullptr; c.h_out = nullptr;
             c.rep_base = c.rep_binom = c.dd_a = c.dd_b = nullptr;

@@ -273,9 +273,10 @@ def test_reference_shaped_list_states(pqb, ref):
     for i, b in enumerate(ins):
         for j, a in enumerate(outs[i]):
             assert relerr(res2[i][j], ref.bbfg_repeated(U, a, b, True)) < TOL
-    # the class a reference user constructs (Boson_Sampling_Utilities.py:30-91) accepts the same shapes
-    res3 = pqb.BBFGRepeatedPermanentCalculatorDouble(U, ins, outs).calculate()
-    assert relerr(res3[1][0], res[1][0]) == 0.0
+    # the class a reference user constructs (Boson_Sampling_Utilities.py:30-91) refuses lists whose items
+    # are not arrays, as the reference does
+    with pytest.raises(Exception, match="should be a numpy array, or a list of numpy arrays"):
+        pqb.BBFGRepeatedPermanentCalculatorDouble(U, ins, outs)
 
 
 def test_double_double_repeated_mode(pqb, ref):

@@ -24,17 +24,16 @@ print(json.dumps({"shots": shots, "ndev": best[1]["ndev"], "call_ms": best[0] * 
                   "launches": best[1]["launches"], "checksum": int(np.array(res).astype(np.int64).dot(np.arange(40)).sum())}))
 """ % ROOT
 ndevs = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "1").split(",")]
-for shots in (125, 1000, 20000):
+shot_list = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "125,1000,20000").split(",")]
+settings = [{}]                                   # the library's own choice
+for tail in ("0", "2", "3", "4", "5"):
+    settings.append({"PQB200_LAP_TAIL": tail})
+settings.append({"PQB200_LAP_TAIL": "3", "PQB200_LAP_WAVES": "1"})
+for shots in shot_list:
     for nd in ndevs:
-        for cl in ("auto", "1", "2", "4", "8"):
-            for wv in ("auto", "1", "4"):
-                for ch in ("8", "4"):
-                    if (wv != "auto" or ch != "8") and cl not in ("auto", "1"):
-                        continue
-                    env = dict(os.environ)
-                    if cl != "auto": env["PQB200_LAP_CLUSTER"] = cl
-                    if wv != "auto": env["PQB200_LAP_WAVES"] = wv
-                    env["PQB200_LAP_CHUNKS"] = ch
-                    r = subprocess.run([sys.executable, "-c", CHILD, str(shots), str(nd)], capture_output=True, text=True, env=env)
-                    line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:]
-                    print(f"cluster={cl} waves={wv} chunks={ch} {line}", flush=True)
+        for st in settings:
+            env = dict(os.environ)
+            env.update(st)
+            r = subprocess.run([sys.executable, "-c", CHILD, str(shots), str(nd)], capture_output=True, text=True, env=env)
+            line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:]
+            print(f"{st or 'default'} {line}", flush=True)
