@@ -72,13 +72,11 @@ struct PowParams {
 };
 
 __host__ __device__ constexpr int pow_group(int c) { return c - 1 >= 4 ? 4 : c - 1 >= 2 ? 2 : 1; }
-// resident CTAs per SM the register budget is set for (measured: tools/rep_cases.py)
-#ifndef PQB_POW_MINB
-#define PQB_POW_MINB(c) ((c) <= 8 ? 3 : (c) <= 26 ? 2 : 1)
-#endif
-__host__ __device__ constexpr int pow_min_blocks(int c) { return PQB_POW_MINB(c); }
 // multiply chains of the straight-line form (measured on C4-shaped problems: the count matters little)
-__host__ __device__ constexpr int pow_chains(int c) { return c >= 36 ? 4 : c >= 4 ? 2 : 1; }
+#ifndef PQB_POW_CHAINS
+#define PQB_POW_CHAINS(c) ((c) >= 36 ? 4 : (c) >= 4 ? 2 : 1)
+#endif
+__host__ __device__ constexpr int pow_chains(int c) { return PQB_POW_CHAINS(c); }
 
 template <int C>
 __device__ __forceinline__ double2 pow_elem(const PowParams<C>& p, int row, int j) {
@@ -140,7 +138,9 @@ __device__ __forceinline__ void pow_term_toggle_single(const PowParams<C>& p, in
     cr[C - 1] = fma(sg, pow_elem<C>(p, row, C - 1).x, cr[C - 1]);
     acc_re = fma(qr[0], f, acc_re);
     acc_im = fma(qi[0], f, acc_im);
+#ifndef PQB_POW_NOABS
     acc_abs = fma(fabs(qr[0]) + fabs(qi[0]), fabs(f), acc_abs);
+#endif
 }
 
 // The general form, acc += w * prod_j c[j]^cm[j]: the complex columns are handled in groups of G, one

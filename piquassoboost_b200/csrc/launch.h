@@ -36,6 +36,12 @@ constexpr int kPowTableSize = 64;
 #define PQB_HD
 #endif
 PQB_HD constexpr int pow_row_stride(int c) { return c % 16 == 0 ? c + 1 : c; }
+// resident CTAs per SM the kernel's register budget is set for (its __launch_bounds__), also what the
+// host plans the chunk decomposition with
+#ifndef PQB_POW_MINB
+#define PQB_POW_MINB(c) ((c) <= 8 ? 3 : (c) <= 26 ? 2 : 1)
+#endif
+PQB_HD constexpr int pow_min_blocks(int c) { return PQB_POW_MINB(c); }
 // steps per chunk that fit the parameter bank next to an R x C matrix (10 bytes per step)
 inline int pow_len_max(int R, int C) {
     const int v = (kPowBufBytes - 16 * R * pow_row_stride(C) - 64) / 10;

@@ -527,10 +527,11 @@ double plain_work(size_t rows, size_t cols) {
     return ldexp(1.0, (int)rows - 1) * 5.5 * (double)plain_kernel_cols((int)rows, (int)cols);
 }
 
-// FP64 instructions of S photon steps with at most `photons` photons each (upper bound: all
-// occupations distinct): used only to choose the device count of an automatic call
+// FP64 instructions of S photon steps with at most `photons` photons each: the bound for all-distinct
+// occupations (2^photons x 14 x photons) scaled by the measured effect of collisions (C5: 1.1e8 Gray terms
+// per 1000 shots instead of 5e8); used only to choose the device count of an automatic call
 double laplace_work(double S, double photons) {
-    return S * ldexp(14.0 * photons, (int)std::min(photons, 60.0) - 1);
+    return 0.2 * S * ldexp(14.0 * photons, (int)std::min(photons, 60.0) - 1);
 }
 
 const RepLimits kRepLimits = {kPowMaxDigits, kPowMaxC, 254, kPowBufBytes, 32, kMaxPlainN};
@@ -876,7 +877,7 @@ static int repeated_locked(Lease& ls, const double* a, size_t rows, size_t cols,
     int maxr = 1;
     for (int m : pr.r) maxr = std::max(maxr, m);
     const int bstride = maxr + 1;
-    rep_plan(pr, ls[0].sm_count * kPlainThreads * 2, (unsigned long long)used,
+    rep_plan(pr, ls[0].sm_count * kPlainThreads * pow_min_blocks(pr.C), (unsigned long long)used,
              (unsigned int)pow_len_max(pr.R, pr.C), bstride, pl);
     if ((unsigned long long)used > pl.nchunks) used = (int)pl.nchunks;
     std::vector<double> parts(5 * (size_t)used);

@@ -180,9 +180,13 @@ def test_double_double_evaluation_matches_reference_long_double(pqb, ref):
     assert relerr(v, ref.bbfg(A, True)) < 1e-15
     gold = _golden_dd()
     A = haar_unitary(32, 32)
-    v, parts = permanent_double_double(A)
+    v, parts = permanent_double_double(A, ndev=1)
     assert relerr(v, complex(*gold["32"]["ref_long_double"])) < 5e-15  # the long double's own error
-    assert [float(x).hex() for x in parts] == gold["32"]["dd_parts_hex"]  # deterministic, bit for bit
+    # deterministic, bit for bit, for a given device count (the golden value was made on one GPU; on more
+    # devices the low words of the partial sums are grouped differently: the high words stay the same)
+    assert [float(x).hex() for x in parts] == gold["32"]["dd_parts_hex"]
+    v2, parts2 = permanent_double_double(A)
+    assert [float(x).hex() for x in parts2[0::2]] == gold["32"]["dd_parts_hex"][0::2]
 
 
 @pytest.mark.parametrize("n,tol", [(30, 1e-11), (34, 1e-11), (36, 1e-11), (38, 5e-11), (40, 5e-11)])
