@@ -6,9 +6,9 @@ Inputs (both produced by committed scripts):
     as four hex doubles, and for n <= 30 the unmodified reference's long double value computed in the
     same run (oracle/_ref);
   * the JSON written by `python tools/ref_big.py 32 34 36` in the dev container: the unmodified
-    reference's long double BBFG calculator on the same matrices (96 s / 423 s / 1861 s on 8 cores).
+    reference's long double BBFG calculator on the same matrices (96 s / 423 s / 1861 s on 8 cores; `tools/ref_big.py 38`: 7594 s).
 
-usage: python tools/make_dd_golden.py gpurun_out/accuracy.jsonl scratch/ref_big_32_34_36.json
+usage: python tools/make_dd_golden.py gpurun_out/accuracy.jsonl tests/golden/inputs/ref_big_32_34_36.json tests/golden/inputs/ref_big_38.json
 (the "40_sub80" case is appended from the output of tools/accuracy_subblock.py 40)
 """
 import json
@@ -18,7 +18,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def main(acc_path, ref_path):
+def main(acc_path, *ref_paths):
     out = {"_comment": "Double-double (106-bit) GPU evaluation pqb200_permanent_dd of "
                        "scipy.stats.unitary_group.rvs(n, random_state=n); dd_parts_hex = re.hi re.lo im.hi im.lo. "
                        "ref_long_double = the unmodified reference's long double BBFG calculator on the same matrix "
@@ -33,7 +33,10 @@ def main(acc_path, ref_path):
             c["ref_long_double"] = r["ref_long_double"]
             c["dd_rel_err_vs_ref"] = r["dd_rel_err_vs_ref"]
         out["cases"][str(r["n"])] = c
-    for n, r in json.load(open(ref_path)).items():
+    refs = {}
+    for ref_path in ref_paths:
+        refs.update(json.load(open(ref_path)))
+    for n, r in refs.items():
         if n not in out["cases"]:
             continue
         v = complex(r["re_f"], r["im_f"])
@@ -50,4 +53,4 @@ def main(acc_path, ref_path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], *sys.argv[2:])
