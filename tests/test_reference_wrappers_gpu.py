@@ -109,3 +109,31 @@ def test_python_mirror_matches_the_reference_wrapper_list_branches(refwrap):
             refwrap.BBFGRepeatedPermanentCalculatorDouble(U, *bad)
         with pytest.raises(Exception, match="should be a numpy array, or a list of numpy arrays"):
             pqb.BBFGRepeatedPermanentCalculatorDouble(U, *bad)
+
+
+@needs_dropin
+def test_reference_strategy_wrappers_on_the_engine(ref):
+    """SURVEY call stack 3.3: the reference's three B-strategy wrapper MODULES
+    (sampling/simulation_strategies/GeneralizedCliffordsB*SimulationStrategy_wrapper.cpp, compiled unmodified)
+    over include/dropin/CGeneralizedCliffordsB*SimulationStrategy.h -> libpqb200.so: seeded shots must be
+    identical to the unmodified reference's own C++ strategies (oracle/_ref), as tuples of int64 arrays."""
+    if DROPIN not in sys.path:
+        sys.path.insert(0, DROPIN)
+    import importlib
+    pkg = "piquassoboost.sampling.simulation_strategies."
+    B = importlib.import_module(pkg + "GeneralizedCliffordsBSimulationStrategy_wrapper").GeneralizedCliffordsBSimulationStrategy_wrapper
+    UL = importlib.import_module(pkg + "GeneralizedCliffordsBUniformLossesSimulationStrategy_wrapper").GeneralizedCliffordsBUniformLossesSimulationStrategy_wrapper
+    LO = importlib.import_module(pkg + "GeneralizedCliffordsBLossySimulationStrategy_wrapper").GeneralizedCliffordsBLossySimulationStrategy_wrapper
+    U = np.ascontiguousarray(haar_unitary(10, 77))
+    state = np.array([1, 1, 1, 0, 1, 0, 2, 0, 0, 0], dtype=np.int64)
+    sim = B(interferometer_matrix=U, seed=123, lib=0)
+    got = sim.simulate(state, 40)
+    assert isinstance(got, tuple) and len(got) == 40 and got[0].dtype == np.int64
+    assert np.array_equal(np.array(got), ref.simulate_B(U, 123, state, 40))
+    sim.seed(9)                                                     # .seed(K) then simulate again
+    assert np.array_equal(np.array(sim.simulate(state, 25)), ref.simulate_B(U, 9, state, 25))
+    ul = UL(interferometer_matrix=U, transmissivity=0.8, seed=5, lib=0)
+    assert np.array_equal(np.array(ul.simulate(state, 60)), ref.simulate_B_uniform_losses(U, 5, state, 60, 0.8))
+    M = np.ascontiguousarray(U * np.linspace(0.7, 1.0, 10)[None, :])  # a lossy (sub-unitary) interferometer
+    lo = LO(interferometer_matrix=M.copy(), approximated_modes=3, seed=11, lib=0)
+    assert np.array_equal(np.array(lo.simulate(state, 50)), ref.simulate_B_lossy(M.copy(), 11, state, 50, 3))
