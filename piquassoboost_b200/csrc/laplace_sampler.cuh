@@ -124,11 +124,17 @@ __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xo
 // lanes per Gray term for a step with N columns
 __host__ __device__ __forceinline__ int lap_lanes(int N) { return N <= 10 ? 1 : N <= 20 ? 2 : 4; }
 
-// instantiation id of a step with N columns: LP = 1 -> NC = 2,4,..,10 (ids 1..5); LP = 2 -> NC = 6..10
-// (ids 11..15); LP = 4 -> NC = 6..10 (ids 21..25)
+// Instantiation of a step with N columns: (NC columns per lane, LP lanes per term), NC * LP >= N (the
+// padding columns hold the constant 1).  The light early steps share ONE instantiation per lane count
+// -- (10,1) for N <= 10, (8,2) for N <= 16: with three CTAs per SM in different photon steps, a separate
+// instantiation per column count thrashed the instruction cache (ncu: stall "no_instruction" 1.8 per
+// issue over the launch of the light steps, profiles/ncu_sampler_c5_r2.md); the extra columns cost
+// nothing there (<= 2^15 Gray terms).  From N = 17 on NC is the exact ceil(N / LP).
 __host__ __device__ __forceinline__ int lap_bucket(int N) {
-    const int lp = lap_lanes(N);
-    return lp == 1 ? (N + 1) / 2 : lp == 2 ? 5 + (N + 1) / 2 : 15 + (N + 3) / 4;
+    if (N <= 10) return 5;    // (10,1)
+    if (N <= 16) return 13;   // (8,2)
+    if (N <= 20) return 5 + (N + 1) / 2;    // (9,2), (10,2)
+    return 15 + (N + 3) / 4;  // (6,4) .. (10,4)
 }
 
 // One Gray sweep of the current step: fills sh.addend[0..N) (unscaled by 2^-(K-1)).
@@ -518,16 +524,8 @@ __global__ void __launch_bounds__(kLapThreads, 3) laplace_sampler_kernel(const L
             __syncthreads();
         } else {
             switch (lap_bucket(N)) {
-                // one lane per term: NC = 2,4,..,10
-                case 1: lap_sweep<2, 1>(sh, crank, csize); break;
-                case 2: lap_sweep<4, 1>(sh, crank, csize); break;
-                case 3: lap_sweep<6, 1>(sh, crank, csize); break;
-                case 4: lap_sweep<8, 1>(sh, crank, csize); break;
-                case 5: lap_sweep<10, 1>(sh, crank, csize); break;
-                // two lanes per term: N = 11..20 -> NC = 6..10
-                case 11: lap_sweep<6, 2>(sh, crank, csize); break;
-                case 12: lap_sweep<7, 2>(sh, crank, csize); break;
-                case 13: lap_sweep<8, 2>(sh, crank, csize); break;
+                case 5: lap_sweep<10, 1>(sh, crank, csize); break;   // N <= 10
+                case 13: lap_sweep<8, 2>(sh, crank, csize); break;   // N = 11..16
                 case 14: lap_sweep<9, 2>(sh, crank, csize); break;
                 case 15: lap_sweep<10, 2>(sh, crank, csize); break;
                 // four lanes per term: N = 21..40 -> NC = 6..10
