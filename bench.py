@@ -102,6 +102,7 @@ def cpu_reference_rate(n_target, budget_s, long_double=True):
         kind, cores = "port", oraclebind.threads()
         fn = lambda a: oraclebind.bbfg(a, oraclebind.LONG_DOUBLE if long_double else oraclebind.DOUBLE)
     n = 18
+    fn(haar(n))                                            # untimed: thread pool start-up, page-in
     t0 = time.perf_counter(); fn(haar(n)); dt = time.perf_counter() - t0
     rate = (2.0 ** (n - 1)) / max(dt, 1e-6) * n          # row-updates x columns per second ~ const
     while n < min(n_target, 34):

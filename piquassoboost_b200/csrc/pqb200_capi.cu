@@ -191,9 +191,8 @@ int grow(void** p, size_t* cap, size_t need) {
 }
 
 
-// caller holds g_mu.  Creates the slot (stream, workspaces) on first use only, so that a
-// one-process-per-GPU job touches nothing but its own device.
-int get_device(int dev, int slot, DeviceCtx** out) {
+// caller holds g_mu.  Counts the visible devices (no context is created).
+int ensure_visible() {
     fill_tables();
     if (g_visible < 0) {
         int visible = 0;
@@ -204,6 +203,15 @@ int get_device(int dev, int slot, DeviceCtx** out) {
                             (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
         g_visible = std::min(visible, kMaxDevices);
     }
+    return PQB200_OK;
+}
+
+// caller holds g_mu.  Creates the slot (stream, workspaces) on first use only, so that a
+// one-process-per-GPU job touches nothing but its own device.  Changes the calling thread's current
+// device (callers restore it: Lease).
+int get_device(int dev, int slot, DeviceCtx** out) {
+    int rc = ensure_visible();
+    if (rc) return rc;
     if (dev < 0 || dev >= g_visible) return fail(PQB200_ERR_ARG, "device index out of range");
     if (slot < 0 || slot >= kSlotsPerDevice) return fail(PQB200_ERR_ARG, "slot index out of range");
     DeviceCtx& c = g_slots[dev][slot];
@@ -234,7 +242,7 @@ int get_device(int dev, int slot, DeviceCtx** out) {
 
 // caller holds g_mu
 int init_locked(int ndev) {
-    int rc = get_device(0, 0, nullptr);
+    int rc = ensure_visible();
     if (rc) return rc;
     if (ndev <= 0 || ndev > g_visible) ndev = g_visible;
     g_default_ndev = ndev;
@@ -258,7 +266,8 @@ struct Lease {
             c->mu.unlock();
         }
         slots.clear();
-        if (saved_dev >= 0) cudaSetDevice(saved_dev);
+        int cur = -1;
+        if (saved_dev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != saved_dev) cudaSetDevice(saved_dev);
         saved_dev = -1;
     }
     int size() const { return (int)slots.size(); }
@@ -296,6 +305,7 @@ int slot_prepare(DeviceCtx& c) {
 int acquire(int ndev, double work, Lease& ls) {
     int used, pref = 0;
     bool roam = false;
+    cudaGetDevice(&ls.saved_dev);  // before anything below changes it: restored when the lease ends
     {
         std::lock_guard<std::mutex> lk(g_mu);
         if (g_default_ndev == 0) {
@@ -309,7 +319,6 @@ int acquire(int ndev, double work, Lease& ls) {
         } else {
             used = std::min(ndev, g_visible);
         }
-        cudaGetDevice(&ls.saved_dev);
         if (used == 1) {
             pref = ls.saved_dev;
             if (pref < 0 || pref >= (roam ? g_default_ndev : g_visible)) pref = 0;
@@ -361,9 +370,9 @@ int acquire(int ndev, double work, Lease& ls) {
 
 // lock one given slot (the one-process-per-GPU entry points name their device)
 int acquire_device(int device, Lease& ls) {
+    cudaGetDevice(&ls.saved_dev);
     {
         std::lock_guard<std::mutex> lk(g_mu);
-        cudaGetDevice(&ls.saved_dev);
         int rc = get_device(device, 0, nullptr);
         if (rc) return rc;
     }
