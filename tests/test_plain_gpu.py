@@ -250,3 +250,28 @@ def test_n40_haar_submatrix_vs_committed_double_double(pqb):
     want = complex(*[float.fromhex(x) for x in gold["dd_parts_hex"]][0::2])
     A = np.ascontiguousarray(unitary_group.rvs(80, random_state=80)[:40, :40])
     assert relerr(pqb.GlynnPermanent(A).calculate(), want) < 1e-11
+
+
+def test_random_shapes_single_and_batched_against_the_oracle(pqb):
+    """200 random shapes incl. the reference's trivial branches (empty -> 1, one row -> product,
+    rows >= cols + 2 -> 0) and rectangular input, each through the single-matrix call and all of them
+    through ONE list-of-matrices call (GlynnPermanentCalculator_Wrapper.hpp:204-293), against the C
+    restatement of the reference (long double)."""
+    from oracle import oraclebind
+    rng = np.random.default_rng(77)
+    mats = []
+    for k in range(200):
+        rows, cols = int(rng.integers(1, 13)), int(rng.integers(1, 13))
+        mats.append(np.ascontiguousarray(rng.normal(size=(rows, cols)) + 1j * rng.normal(size=(rows, cols))))
+    want = [oraclebind.bbfg(m, oraclebind.LONG_DOUBLE) for m in mats]
+    batched = pqb.BBFGPermanentDouble(mats).calculate()
+    assert len(batched) == len(mats)
+    for m, w, b in zip(mats, want, batched):
+        single = pqb.BBFGPermanentLongDouble(m).calculate()
+        scale = max(abs(w), 1e-12)
+        assert abs(single - w) <= 1e-11 * scale, (m.shape, single, w)
+        assert abs(b - w) <= 1e-11 * scale, (m.shape, b, w)
+    # a non-contiguous view goes through the same conversion as in the reference wrapper
+    big = haar_unitary(14, 3)
+    view = big[::2, ::2]
+    assert relerr(pqb.GlynnPermanent(view).calculate(), oraclebind.bbfg(np.ascontiguousarray(view), oraclebind.LONG_DOUBLE)) < 1e-12

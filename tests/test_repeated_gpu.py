@@ -256,6 +256,42 @@ def test_every_power_kernel_instantiation(pqb, ref, C):
             assert relerr(got, ref.bbfg_repeated(U, inp, out, True)) < 1e-10
 
 
+def test_random_stress_against_the_oracle(pqb):
+    """300 random shapes: rectangular matrices, zero occupations, one-sided bunching, both orientations of
+    the Gray space, the trivial branches -- single calls and one batched call, against the C restatement
+    of the reference (long double; pinned to the reference in tests/test_oracle.py)."""
+    from oracle import oraclebind
+    rng = np.random.default_rng(2024)
+    cases = []
+    for k in range(300):
+        rows, cols = int(rng.integers(1, 10)), int(rng.integers(1, 10))
+        photons = int(rng.integers(0, 13))
+        A = rng.normal(size=(rows, cols)) + 1j * rng.normal(size=(rows, cols))
+        pr = rng.dirichlet(np.ones(rows) * rng.choice([0.2, 1.0, 5.0]))
+        pc = rng.dirichlet(np.ones(cols) * rng.choice([0.2, 1.0, 5.0]))
+        out = rng.multinomial(photons, pr).astype(np.int64)     # row multiplicities
+        inp = rng.multinomial(photons, pc).astype(np.int64)     # column multiplicities
+        cases.append((np.ascontiguousarray(A), inp, out))
+    for A, inp, out in cases:
+        want = oraclebind.bbfg_repeated(A, inp, out, oraclebind.LONG_DOUBLE)
+        got = pqb.BBFGRepeatedPermanentCalculatorDouble(A, inp, out).calculate()
+        if abs(want) < 1e-12:
+            assert abs(got - want) < 1e-11, (A.shape, inp, out, got, want)
+        else:
+            assert relerr(got, want) < 1e-10, (A.shape, inp, out, got, want)
+    # the batched entry point on one matrix with many occupation pairs (kernel jobs, trivial jobs, single
+    # rows), in the reference's per-input form: every input with the outputs of the same photon number
+    U = haar_unitary(9, 99)
+    ins = [rng.multinomial(p, rng.dirichlet(np.ones(9))).astype(np.int64) for p in rng.integers(0, 11, size=60)]
+    outs = [[b for b in ins if b.sum() == a.sum()] for a in ins]
+    res = pqb.ChinHuhPermanentCalculator_wrapper(7, U, ins, outs).calculate()
+    assert [len(r) for r in res] == [len(o) for o in outs]
+    for i, a in enumerate(ins):
+        for j, b in enumerate(outs[i]):
+            want = oraclebind.bbfg_repeated(np.ascontiguousarray(U), a, b, oraclebind.LONG_DOUBLE)
+            assert abs(res[i][j] - want) <= 1e-10 * max(abs(want), 1e-12), (a, b, res[i][j], want)
+
+
 def test_reference_shaped_list_states(pqb, ref):
     """ChinHuhPermanentCalculator_Wrapper.hpp:233-326: input_state a list of n vectors, output_state a list
     of n (ragged) lists of vectors -> ret[i][j]; and the 'multiInput' form the other way round."""
