@@ -37,7 +37,8 @@ inline void check(int rc) {
     if (rc != PQB200_OK) throw std::string(pqb200_last_error());
 }
 
-/// number of GPUs a single calculate() is sharded over (0 = all)
+/// `ndev` handed to the C ABI by every shim: 0 = automatic (the library sizes the device count from the work
+/// of the call: small permanents run on ONE GPU, an n=40 permanent on all of them; include/pqb200.h)
 inline int& default_ndev() {
     static int n = 0;
     return n;
@@ -82,7 +83,9 @@ public:
 
 class BBFGPermanentCalculatorRepeated {
 public:
-    /// col_mult = input state, row_mult = output state (reference argument order)
+    /// col_mult = input state, row_mult = output state (reference argument order).  Power form as in the
+    /// reference (no photon-number cap); ill-conditioned inputs are re-evaluated in double-double by the
+    /// library itself (pqb200_last_repeated_bound tells), use_inf forces that mode.
     template <class Matrix, class State>
     Complex16 calculate(Matrix& mtx, State& col_mult, State& row_mult, bool use_extended = false,
                         bool use_inf = false) {
