@@ -1,8 +1,10 @@
-// repeated_host.h -- host-side preparation of a repeated-row permanent for glynn_repeated_kernel:
-// the reference's filtering / anchor-row step, the orientation choice, the physical expansion of
-// the product side, and the per-chunk step table (toggled row, direction for both high parities,
-// signed binomial weight).  Pure integer / table work; all floating-point summation happens on the
-// GPU except the two `base` vectors (sums of at most D rows, formed in long double).
+// repeated_host.h -- host-side preparation of a repeated-row / repeated-column permanent for
+// glynn_reppow_kernel and the double-double walk (dd_repeated.cu): the reference's filtering / anchor-row
+// step, the orientation choice, the compact (power-form) matrix with the product side's columns sorted
+// by multiplicity, the unit-modulus normalisation, and the per-chunk step table (toggled row, direction
+// for both high parities, signed binomial weight).  Pure integer / table work; all floating-point
+// summation happens on the GPU except the two `base` vectors (sums of at most D rows, formed in long
+// double).
 #pragma once
 #include <stdint.h>
 
