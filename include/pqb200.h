@@ -131,8 +131,9 @@ int pqb200_permanent_batch(const double* const* a, const size_t* rows, const siz
  * Returns PQB200_ERR_MISMATCH when the photon numbers differ (the reference throws std::string,
  * BBFGPermanentCalculatorRepeated.hpp:119-124).
  * Evaluated in the reference's power form (column sums raised to their multiplicity, hpp:263-275):
- * no photon-number cap; the limits are 45 distinct rows x 48 distinct columns on the two sides after
- * the orientation choice, and multiplicities <= 254.
+ * no photon-number cap; the fast kernel takes 45 distinct rows x 48 distinct columns on the two sides after
+ * the orientation choice (wider shapes, up to 65 x 128, are served by the double-double walk), and
+ * multiplicities <= 254.
  * Precision dispatch: the kernel also returns sum|term|; when the a-posteriori rounding bound
  * eps*(photons+8)*sum|term|/|sum| exceeds 2e-9 the call is re-evaluated in double-double arithmetic
  * (pqb200_permanent_repeated_dd) -- the engine's form of the reference's use_extended / use_inf

@@ -17,8 +17,8 @@
 
 namespace pqb200 {
 
-constexpr int kDDRepMaxN = kPowMaxC;       // distinct product-side columns (multiplicities are powers)
-constexpr int kDDRepMaxD = kPowMaxDigits;
+constexpr int kDDRepMaxN = kDDRepCols;    // distinct product-side columns (multiplicities are powers)
+constexpr int kDDRepMaxD = kDDRepDigits;  // Gray-side rows besides the anchor
 
 struct RepDDParams {
     const double* mat;    // device, R x N interleaved complex; row 0 = anchor, rows 1..D = digit rows

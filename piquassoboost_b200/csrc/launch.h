@@ -29,6 +29,10 @@ constexpr int kPowMaxDigits = 44;   // Gray-side rows besides the anchor
 constexpr int kPowBufBytes = 32128; // matrix + step tables inside the kernel-parameter bank
 constexpr int kPowLenCap = 4096;
 constexpr int kPowTableSize = 64;
+// the double-double walk (dd_repeated.cu) keeps its column sums in local memory: wider limits, which also
+// serve shapes beyond the fast kernel's
+constexpr int kDDRepCols = 128;
+constexpr int kDDRepDigits = 64;
 
 #ifdef __CUDACC__
 #define PQB_HD __host__ __device__

@@ -544,6 +544,8 @@ double laplace_work(double S, double photons) {
 }
 
 const RepLimits kRepLimits = {kPowMaxDigits, kPowMaxC, 254, kPowBufBytes, 32, kMaxPlainN};
+// the double-double walk reads the matrix from global memory and keeps its sums in local memory
+const RepLimits kRepDDLimits = {kDDRepDigits, kDDRepCols, 254, 1 << 30, 0, kDDRepCols};
 
 }  // namespace
 
@@ -833,11 +835,8 @@ int pqb200_permanent_repeated_dd(const double* a, size_t rows, size_t cols, size
     if (rc) return rc;
     RepPrepared pr;
     std::string err;
-    RepLimits lim = kRepLimits;
-    lim.buf_bytes = 1 << 30;  // the double-double walk reads the matrix from global memory
-    lim.max_plain_n = 1 << 20;
-    rc = rep_prepare(a, rows, cols, stride, row_mult, col_mult, lim, pr, err);
-    if (rc) return fail(rc, err);
+    rc = rep_prepare(a, rows, cols, stride, row_mult, col_mult, kRepDDLimits, pr, err);
+    if (rc) return fail(rc == 4 ? PQB200_ERR_ARG : rc, err);
     Lease ls;
     rc = acquire(ndev, pr.trivial ? 0.0 : rep_total_steps(pr) * 200.0 * pr.photons, ls);
     if (rc) return rc;
@@ -869,9 +868,26 @@ static int repeated_locked(Lease& ls, const double* a, size_t rows, size_t cols,
     RepPrepared pr;
     std::string err;
     int rc = rep_prepare(a, rows, cols, stride, row_mult, col_mult, kRepLimits, pr, err);
-    if (rc) return fail(rc, err);
     g_last_bound = 0.0;
     g_last_dd = 0;
+    if (rc == 4) {
+        // beyond the fast kernel's shape limits (more than 48 distinct columns on the product side, more
+        // than 45 rows on the Gray side): the double-double walk takes up to 65 x 128, slowly but exactly
+        RepPrepared wide;
+        std::string err2;
+        if (rep_prepare(a, rows, cols, stride, row_mult, col_mult, kRepDDLimits, wide, err2) != 0)
+            return fail(PQB200_ERR_ARG, err);
+        if (rep_total_steps(wide) > 1e13)
+            return fail(PQB200_ERR_ARG, err + "; the double-double fallback would need more than 1e13 Gray steps");
+        double dd4[4];
+        rc = repeated_dd_prepared(ls, wide, dd4);
+        if (rc) return rc;
+        g_last_dd = 1;
+        out[0] = dd4[0] + dd4[1];
+        out[1] = dd4[2] + dd4[3];
+        return PQB200_OK;
+    }
+    if (rc) return fail(rc, err);
     if (pr.trivial) {
         out[0] = pr.value[0];
         out[1] = pr.value[1];

@@ -44,7 +44,7 @@ struct RepLimits {
 };
 
 // Reference semantics: BBFGPermanentCalculatorRepeated.cpp:74-141 and .hpp:74-140.
-//   returns 0 ok, 3 photon-number mismatch, 2 bad argument (message in err)
+//   returns 0 ok, 3 photon-number mismatch, 2 bad argument, 4 shape beyond `lim` (message in err)
 inline int rep_prepare(const double* a, size_t rows, size_t cols, size_t stride,
                        const int64_t* row_mult, const int64_t* col_mult, const RepLimits& lim,
                        RepPrepared& out, std::string& err) {
@@ -94,8 +94,8 @@ inline int rep_prepare(const double* a, size_t rows, size_t cols, size_t stride,
         const bool fit_other = transpose ? fits(ri, row_mult, ci, col_mult) : fits(ci, col_mult, ri, row_mult);
         if (!fit_other) {
             err = "repeated permanent exceeds the limits of this build (at most " + std::to_string(lim.max_rows + 1) +
-                  " distinct rows x " + std::to_string(lim.max_cols) + " distinct columns resident in the kernel-parameter bank)";
-            return 2;
+                  " distinct rows x " + std::to_string(lim.max_cols) + " distinct columns)";
+            return 4;
         }
         transpose = !transpose;
     }
@@ -164,7 +164,7 @@ inline int rep_prepare(const double* a, size_t rows, size_t cols, size_t stride,
     if (out.plain_route && out.N > lim.max_plain_n) {
         err = "matrix dimension exceeds " + std::to_string(lim.max_plain_n) +
               " (kernel-parameter resident matrix limit of this build)";
-        return 2;
+        return 4;
     }
     return 0;
 }

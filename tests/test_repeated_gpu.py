@@ -219,12 +219,23 @@ def test_sixty_photons_in_ten_modes(pqb, ref):
     out = np.array([3] * 10 + [0] * 2)
     got = pqb.BBFGRepeatedPermanentCalculatorDouble(V, inp, out).calculate()
     assert relerr(got, _truth(V, inp, out)) < 1e-10
+    # more distinct columns than the fast kernel keeps in registers (48): 60 single photons from 60 input modes
+    # bunched into three output modes -- served by the double-double walk (up to 65 x 128), exactly
+    from piquassoboost_b200 import _lib
+    W = haar_unitary(60, 612)
+    inp = np.ones(60, dtype=np.int64)
+    out = np.zeros(60, dtype=np.int64)
+    out[:3] = [20, 20, 20]
+    got = pqb.BBFGRepeatedPermanentCalculatorDouble(W, inp, out).calculate()
+    assert _lib.last_repeated_bound()[1]                      # went through the double-double mode
+    assert relerr(got, _truth(W, inp, out)) < 1e-12
+    with pytest.raises(Exception, match="exceeds the limits"):  # 2^59 Gray steps either way round
+        pqb.BBFGRepeatedPermanentCalculatorDouble(W, inp, inp.copy()).calculate()
     # 60 photons over all 10 modes on BOTH sides (about 7^10 Gray steps): against the reference's long double
     inp = np.array([6] * 10)
     out = np.array([7, 5, 6, 6, 8, 4, 6, 6, 5, 7])
     got = pqb.BBFGRepeatedPermanentCalculatorDouble(U, inp, out).calculate()
     want = ref.bbfg_repeated(U, inp, out, True)
-    from piquassoboost_b200 import _lib
     bound, used_dd = _lib.last_repeated_bound()
     # the long double reference is itself only accurate to ~1e-19 x condition number here
     assert relerr(got, want) < max(1e-10, 1e-3 * bound), (got, want, bound, used_dd)
