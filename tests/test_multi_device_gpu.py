@@ -130,8 +130,12 @@ def test_async_shard_on_the_default_stream(pqb):
     from piquassoboost_b200.distributed import permanent_distributed
     A = haar_unitary(27, 27)
     want = pqb.GlynnPermanentCalculator_wrapper(A, 7, ndev=1).calculate()
-    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    os.environ.setdefault("MASTER_PORT", "29731")
+    import socket
+    with socket.socket() as sk:                       # a free port: nothing else on the box may hold it
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(0)
     dist.init_process_group("nccl", rank=0, world_size=1)
     try:
