@@ -478,6 +478,9 @@ __global__ void __launch_bounds__(kLapThreads, 3) laplace_sampler_kernel(const L
     __shared__ LapShared sh;
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned int csize = cluster.num_blocks(), crank = cluster.block_rank();
+    // every CTA of the cluster must be running before any of them touches another one's shared memory
+    // (the first photon step has no sweep, hence no barrier of its own, before rank 0 publishes the draw)
+    if (csize > 1) cluster.sync();
     const int tid = threadIdx.x, m = a.m;
     const int slot = (int)(blockIdx.x / csize);
     const int s = a.order ? a.order[slot] : slot;
