@@ -116,6 +116,8 @@ struct LapShared {
     int lowPar[2];
     int R, N, q, K, chosen;
     unsigned char sample[256], cur[256];
+    double rnd[kLapMaxPhotons];        // the shot's uniform draws and insertion order, fetched once (mode 0):
+    unsigned char ins[kLapMaxPhotons]; // a global load per photon step would sit on the critical path
     unsigned char gidx[kLapMaxPhotons], radix[kLapMaxPhotons], pidx[kLapMaxPhotons], first[kLapMaxPhotons];
 };
 
@@ -492,6 +494,10 @@ __global__ void __launch_bounds__(kLapThreads, 3) laplace_sampler_kernel(const L
         k_first = a.step_begin < np ? a.step_begin : np;
         steps = a.step_end < np ? a.step_end : np;
         if (k_first >= steps && a.step_begin > 0) return;  // the shot was finished by an earlier launch (uniform per cluster)
+        if (tid < steps) {
+            sh.rnd[tid] = a.rnd[(size_t)s * a.nmax + tid];
+            sh.ins[tid] = a.ins[(size_t)s * a.nmax + tid];
+        }
         if (k_first == 0) {
             for (int i = tid; i < m; i += kLapThreads) sh.sample[i] = sh.cur[i] = 0;
         } else {
@@ -514,7 +520,7 @@ __global__ void __launch_bounds__(kLapThreads, 3) laplace_sampler_kernel(const L
     for (int k = k_first; k < steps; k++) {
         if (a.mode == 0) {
             // update_input_by_single_photon (samplingHelperFunctions.cpp:377-406), order pre-resolved
-            if (tid == 0) sh.cur[a.ins[(size_t)s * a.nmax + k]]++;
+            if (tid == 0) sh.cur[sh.ins[k]]++;
             __syncthreads();
         }
         lap_prepare(sh, a, csize LAP_T0_ARG);
@@ -625,7 +631,7 @@ __global__ void __launch_bounds__(kLapThreads, 3) laplace_sampler_kernel(const L
                         const double o = __shfl_up_sync(FULL, incl, off);
                         if (tid >= off) incl += o;
                     }
-                    const double r = a.rnd[(size_t)s * a.nmax + k];
+                    const double r = sh.rnd[k];
                     double acc = incl - run;
                     int hit = -1;
 #pragma unroll
