@@ -50,9 +50,12 @@ inline int lap_cluster_for(size_t shots, int sm_count) {
     }
     // measured (tools/sampler_sweep.py, profiles/sampler_sweep_r2.log): every CTA of a cluster repeats the
     // per-step preparation, so splitting only pays while it fills otherwise idle SMs
+    // so: the largest cluster whose CTAs are all resident at once; clusters of 8 synchronise more dearly and
+    // only pay with SMs to spare (measured kernel ms for 25 / 50 / 100 / 200 shots of C5 at 1, 2, 4, 8 CTAs
+    // per shot: 1.40 0.86 0.58 0.48 / 1.63 0.99 0.69 0.78 / 1.75 1.13 0.83 1.22 / 1.87 1.27 1.36 2.03)
     const size_t slots = (size_t)sm_count * 3;
     int cs = 1;
-    while (cs < 8 && shots * (size_t)cs * 2 <= slots) cs *= 2;
+    while (cs < 8 && shots * (size_t)cs * 2 <= (cs == 4 ? slots * 2 / 3 : slots)) cs *= 2;
     return cs;
 }
 

@@ -1,0 +1,28 @@
+cat > /tmp/cs.py <<'PY'
+import os, sys, time, json, subprocess
+ROOT = os.getcwd()
+CHILD = r"""
+import os, sys, time
+sys.path.insert(0, %r)
+import numpy as np
+from scipy.stats import unitary_group
+import piquassoboost_b200 as pqb
+U = np.ascontiguousarray(unitary_group.rvs(40, random_state=5))
+state = np.array([1] * 20 + [0] * 20, dtype=np.int64)
+out = []
+for shots in (25, 50, 100, 200):
+    sim = pqb.GeneralizedCliffordsBSimulationStrategy(U, seed=5, ndev=1)
+    sim.simulate(state, shots)
+    best = 1e9
+    for r in range(5):
+        sim.seed(5); sim.simulate(state, shots); best = min(best, pqb.last_stats()["kernel_ms"])
+    out.append("%%d:%%.3f" %% (shots, best))
+print(os.environ.get("PQB200_LAP_CLUSTER", "auto"), " ".join(out))
+""" % ROOT
+for cl in ("auto", "1", "2", "4", "8"):
+    env = dict(os.environ)
+    if cl != "auto": env["PQB200_LAP_CLUSTER"] = cl
+    r = subprocess.run([sys.executable, "-c", CHILD], capture_output=True, text=True, env=env)
+    print(r.stdout.strip() or r.stderr[-300:], flush=True)
+PY
+python /tmp/cs.py
