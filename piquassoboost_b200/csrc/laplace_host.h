@@ -21,7 +21,7 @@ struct LapLaunch {
     double* d_pmf;
     unsigned long long* d_gray_terms;
     const int* d_order;  // [shots] shot index handled by cluster i (NULL = identity)
-    int cluster;         // CTAs per shot: 1, 2, 4 or 8
+    int cluster;         // CTAs per shot: 1 .. 8
     int chunks_per_owner;  // low/high digit split: chunks aimed at per term owner (0 = default 4, measured)
     unsigned long long* d_prof;  // PQB_LAP_PROFILE builds only
     int step_begin, step_end;    // mode 0: photon steps [step_begin, step_end) of every shot (0, nmax = all)
@@ -46,7 +46,7 @@ inline int lap_tail_steps(size_t shots, int nmax, int sm_count) {
 inline int lap_cluster_for(size_t shots, int sm_count) {
     if (const char* f = getenv("PQB200_LAP_CLUSTER")) {  // tuning aid
         const int v = atoi(f);
-        if (v == 1 || v == 2 || v == 4 || v == 8) return v;
+        if (v >= 1 && v <= 8) return v;
     }
     // measured (tools/sampler_sweep.py, profiles/sampler_sweep_r2.log): every CTA of a cluster repeats the
     // per-step preparation, so splitting only pays while it fills otherwise idle SMs
@@ -54,9 +54,10 @@ inline int lap_cluster_for(size_t shots, int sm_count) {
     // only pay with SMs to spare (measured kernel ms for 25 / 50 / 100 / 200 shots of C5 at 1, 2, 4, 8 CTAs
     // per shot: 1.40 0.86 0.58 0.48 / 1.63 0.99 0.69 0.78 / 1.75 1.13 0.83 1.22 / 1.87 1.27 1.36 2.03)
     const size_t slots = (size_t)sm_count * 3;
-    int cs = 1;
-    while (cs < 8 && shots * (size_t)cs * 2 <= (cs == 4 ? slots * 2 / 3 : slots)) cs *= 2;
-    return cs;
+    if (shots == 0) return 1;
+    size_t cs = slots / shots;  // any size up to the portable limit of 8 is a valid cluster: 125 shots get 3
+    if (cs > 4) cs = shots * 8 * 3 <= slots * 2 ? 8 : 4;
+    return cs < 1 ? 1 : (int)cs;
 }
 
 cudaError_t lap_init_device(void);  // binomial table of the current device

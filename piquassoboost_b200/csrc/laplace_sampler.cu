@@ -75,7 +75,7 @@ cudaError_t lap_launch(const LapLaunch& l, cudaStream_t stream) {
     }
     a.prof = g_prof;
 #endif
-    const int cs = (l.cluster == 2 || l.cluster == 4 || l.cluster == 8) ? l.cluster : 1;
+    const int cs = (l.cluster >= 1 && l.cluster <= kLapMaxCluster) ? l.cluster : 1;
     static_assert(kLapMaxCluster == 8, "cluster sizes");
     if (cs == 1) {  // no cluster: the plain launch
         laplace_sampler_kernel<<<l.shots, kLapThreads, 0, stream>>>(a);

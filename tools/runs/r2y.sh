@@ -10,7 +10,7 @@ import piquassoboost_b200 as pqb
 U = np.ascontiguousarray(unitary_group.rvs(40, random_state=5))
 state = np.array([1] * 20 + [0] * 20, dtype=np.int64)
 out = []
-for shots in (25, 50, 100, 200):
+for shots in (60, 100, 125, 150):
     sim = pqb.GeneralizedCliffordsBSimulationStrategy(U, seed=5, ndev=1)
     sim.simulate(state, shots)
     best = 1e9
@@ -19,7 +19,7 @@ for shots in (25, 50, 100, 200):
     out.append("%%d:%%.3f" %% (shots, best))
 print(os.environ.get("PQB200_LAP_CLUSTER", "auto"), " ".join(out))
 """ % ROOT
-for cl in ("auto", "1", "2", "4", "8"):
+for cl in ("auto", "2", "3", "4", "5", "6"):
     env = dict(os.environ)
     if cl != "auto": env["PQB200_LAP_CLUSTER"] = cl
     r = subprocess.run([sys.executable, "-c", CHILD], capture_output=True, text=True, env=env)
