@@ -92,3 +92,41 @@ def test_many_shots_exercise_the_threaded_host_path(pqb, ref):
     want = ref.simulate_B(U, 5, inp, 300)
     got = np.array(pqb.GeneralizedCliffordsBSimulationStrategy(U, seed=5).simulate(inp, 300))
     assert (got == want).all()
+
+
+def test_waves_and_cost_ordered_second_launch_give_the_same_shots(pqb, ref):
+    """The launch policy (several waves per device, the last photon steps as a second, cost-ordered launch
+    that overlaps the replay of the random stream, clusters of CTAs per shot) must not change a single shot:
+    2600 shots of 12 photons in 16 modes under the default policy, as one plain launch, and with forced
+    clusters / waves, against each other and -- the first 40 -- against the unmodified reference."""
+    import os
+    U = np.ascontiguousarray(haar_unitary(16, 160))
+    state = np.array([1] * 12 + [0] * 4, dtype=np.int64)
+    knobs = ("PQB200_LAP_TAIL", "PQB200_LAP_WAVES", "PQB200_LAP_CLUSTER")
+    saved = {k: os.environ.pop(k, None) for k in knobs}
+
+    def run(shots=2600, **env):
+        for k in knobs:
+            os.environ.pop(k, None)
+        os.environ.update({k: str(v) for k, v in env.items()})
+        sim = pqb.GeneralizedCliffordsBSimulationStrategy(U, seed=77)
+        return np.array(sim.simulate(state, shots)), pqb.last_stats()["launches"]
+
+    try:
+        default, launches = run()
+        assert launches >= 4                                   # two waves x two launches
+        single, launches1 = run(PQB200_LAP_TAIL=0, PQB200_LAP_WAVES=1)
+        assert launches1 == 1
+        assert np.array_equal(default, single)
+        assert np.array_equal(default, run(PQB200_LAP_TAIL=4, PQB200_LAP_WAVES=3)[0])
+        small = run(shots=120)[0]
+        assert np.array_equal(small, default[:120])
+        for cl in (1, 3, 8):
+            assert np.array_equal(run(shots=120, PQB200_LAP_CLUSTER=cl)[0], small)
+        assert np.array_equal(default[:40], ref.simulate_B(U, 77, state, 40))
+        assert np.all(default.sum(axis=1) == 12)
+    finally:
+        for k in knobs:
+            os.environ.pop(k, None)
+            if saved[k] is not None:
+                os.environ[k] = saved[k]
