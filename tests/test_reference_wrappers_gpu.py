@@ -137,3 +137,18 @@ def test_reference_strategy_wrappers_on_the_engine(ref):
     M = np.ascontiguousarray(U * np.linspace(0.7, 1.0, 10)[None, :])  # a lossy (sub-unitary) interferometer
     lo = LO(interferometer_matrix=M.copy(), approximated_modes=3, seed=11, lib=0)
     assert np.array_equal(np.array(lo.simulate(state, 50)), ref.simulate_B_lossy(M.copy(), 11, state, 50, 3))
+
+
+@needs_dropin
+def test_reference_free_function_module_on_the_engine(ref):
+    """sampling/permanent_calculators_wrapper.cpp (permanent_CPU_repeated_double / _long_double), a complete
+    module of the reference compiled unmodified over include/dropin."""
+    if DROPIN not in sys.path:
+        sys.path.insert(0, DROPIN)
+    import importlib
+    mod = importlib.import_module("piquassoboost.sampling.permanent_calculators")
+    U = np.ascontiguousarray(haar_unitary(6, 8))
+    a, b = np.array([2, 1, 0, 1, 0, 1], dtype=np.int64), np.array([0, 0, 3, 1, 1, 0], dtype=np.int64)
+    want = ref.bbfg_repeated(U, a, b, True)
+    assert relerr(mod.permanent_CPU_repeated_double(U, a, b), want) < 1e-12
+    assert relerr(mod.permanent_CPU_repeated_long_double(U, a, b), want) < 1e-12
