@@ -32,9 +32,12 @@ struct LapLaunch {
 
 // Photon steps left to the second, cost-ordered launch of a wave (0: a single launch).
 inline int lap_tail_steps(size_t shots, int nmax, int sm_count) {
-    int tail = 3;
+    // measured (profiles/sampler_sweep_tail_r2s.log, kernel ms at tail 0 / 3 / 4 / 5): 1000 shots 3.9 / 3.18 / 3.11 /
+    // 3.11; 444 shots (every CTA resident at once: the ordered launch still spreads the long shots over the SMs)
+    // 2.30 / - / 2.17; 125 shots (clusters) 0.94 / - / 0.98; waves of 5000 shots 56.7 / 56.8 / 56.0 / 56.1
+    int tail = 4;
     const size_t slots = (size_t)sm_count * 3;
-    if (nmax < 10 || shots <= slots || shots > 6 * slots) tail = 0;  // everything resident at once / enough shots to balance
+    if (nmax < 10 || shots < slots || shots > 6 * slots) tail = 0;  // clusters fill the SMs / enough shots to balance
     if (const char* f = getenv("PQB200_LAP_TAIL")) {  // tuning aid
         const int v = atoi(f);
         if (v >= 0 && v < nmax) tail = v;
@@ -62,5 +65,8 @@ inline int lap_cluster_for(size_t shots, int sm_count) {
 
 cudaError_t lap_init_device(void);  // binomial table of the current device
 cudaError_t lap_launch(const LapLaunch& l, cudaStream_t stream);
+// d_order[rank] = base + i for the `shots` entries of d_cost, descending cost, ties by index (stable): the order
+// of a wave's second launch, formed in-stream so that no host round trip separates the two launches
+cudaError_t lap_order_by_cost(const float* d_cost, int* d_order, int shots, int base, cudaStream_t stream);
 
 }  // namespace pqb200

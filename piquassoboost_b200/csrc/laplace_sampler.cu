@@ -40,6 +40,12 @@ static void lap_prof_report(cudaStream_t stream) {
 }
 #endif
 
+cudaError_t lap_order_by_cost(const float* d_cost, int* d_order, int shots, int base, cudaStream_t stream) {
+    if (shots <= 0) return cudaSuccess;
+    lap_rank_kernel<<<(shots + kLapRankThreads - 1) / kLapRankThreads, kLapRankThreads, 0, stream>>>(d_cost, d_order, shots, base);
+    return cudaGetLastError();
+}
+
 cudaError_t lap_launch(const LapLaunch& l, cudaStream_t stream) {
     if (l.shots <= 0) return cudaSuccess;
     LapArgs a;

@@ -88,7 +88,7 @@ struct LapArgs {
     int step_begin, step_end;
     unsigned char* state;
     float* cost;                     // [shots] Gray terms of the last step a handed-over shot has done: the
-                                     // host orders the next launch by it (longest first)
+                                     // next launch is ordered by it, longest first (lap_rank_kernel)
     const int* nphot;                // [shots] photon steps of the shot                    (mode 0)
     const unsigned char* ins;        // [shots][nmax] input mode of the k-th inserted photon (mode 0)
     const double* rnd;               // [shots][nmax] uniform draw of step k                 (mode 0)
@@ -673,6 +673,31 @@ __global__ void __launch_bounds__(kLapThreads, 3) laplace_sampler_kernel(const L
             for (int i = tid; i < m; i += kLapThreads) a.pmf_out[(size_t)s * m + i] = sh.p[i] / tot;
         }
     }
+}
+
+// Order of the second launch of a wave, formed on the device so that the host can queue both launches of a
+// wave back to back: order[rank] = base + i with the shots ranked by descending cost, ties by ascending index
+// (what a stable sort gives).  S is a few thousand at most: every thread counts the shots ahead of its own
+// against shared-memory tiles of the cost vector.
+constexpr int kLapRankThreads = 256;
+__global__ void __launch_bounds__(kLapRankThreads) lap_rank_kernel(const float* __restrict__ cost, int* __restrict__ order,
+                                                                   const int S, const int base) {
+    __shared__ float tile[kLapRankThreads];
+    const int i = (int)(blockIdx.x * kLapRankThreads + threadIdx.x);
+    const float mine = i < S ? cost[i] : 0.0f;
+    int rank = 0;
+    for (int j0 = 0; j0 < S; j0 += kLapRankThreads) {
+        const int j = j0 + (int)threadIdx.x;
+        tile[threadIdx.x] = j < S ? cost[j] : -1.0f;  // costs are >= 0: the padding ranks behind everything
+        __syncthreads();
+        const int n = S - j0 < kLapRankThreads ? S - j0 : kLapRankThreads;
+        for (int t = 0; t < n; t++) {
+            const float c = tile[t];
+            rank += (c > mine || (c == mine && j0 + t < i)) ? 1 : 0;
+        }
+        __syncthreads();
+    }
+    if (i < S) order[rank] = base + i;
 }
 
 }  // namespace pqb200

@@ -12,7 +12,6 @@
 #include <algorithm>
 #include <chrono>
 #include <mutex>
-#include <random>
 #include <string>
 #include <thread>
 #include <vector>
@@ -25,6 +24,7 @@
 #include "laplace_host.h"
 #include "svd_host.h"
 #include "repeated_host.h"
+#include "rng_replay.h"
 
 using namespace pqb200;
 
@@ -101,7 +101,6 @@ struct DeviceCtx {
     double* h_out = nullptr;  // pinned, 8 doubles
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     std::vector<cudaEvent_t> evs;  // extra timing events (calls that time several separate launches)
-    std::vector<cudaEvent_t> wevs; // per-wave completion events of the sampler
     // Recorded behind work that an asynchronous entry point (pqb200_permanent_shard with d_out,
     // pqb200_permanent_nccl_async) left in flight on a CALLER's stream: every later use of the slot's
     // workspaces is ordered behind it with cudaStreamWaitEvent.
@@ -594,8 +593,6 @@ void pqb200_shutdown(void) {
             cudaEventDestroy(c.busy);
             for (cudaEvent_t e : c.evs) cudaEventDestroy(e);
             c.evs.clear();
-            for (cudaEvent_t e : c.wevs) cudaEventDestroy(e);
-            c.wevs.clear();
             cudaStreamDestroy(c.stream);
             c.partials = nullptr; c.counter = nullptr; c.d_out = nullptr; c.h_out = nullptr;
             c.rep_base = c.rep_binom = c.dd_a = c.dd_b = nullptr;

@@ -180,3 +180,15 @@ def test_repeated_prepare_edge_cases(hl):
     rc, pl = _rep_plan(hl, U, [0, 2, 0, 1], [3, 0, 0, 0], 16)  # one row three times: 3! * prod
     assert rc == 0
     assert relerr(_emulate_repeated_kernel(pl), 6 * U[0, 1] ** 2 * U[0, 3]) < 1e-13
+
+
+def test_rng_replay_header_matches_std_mt19937(tmp_path):
+    """csrc/rng_replay.h (block generator, remainder by multiplication, PDEP / portable photon pick) against
+    std::mt19937 -- the reference's generator (samplingHelperFunctions.cpp:58-74) -- and a plain restatement of
+    the per-step draws: the stream, random_index, random_double_0_1, the photon loops and the stream position
+    after them (tests/cpp/rng_replay.cpp)."""
+    exe = str(tmp_path / "rng_replay")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(ROOT, "tests", "cpp", "rng_replay.cpp")],
+                   check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr

@@ -15,7 +15,7 @@ shots = int(sys.argv[1]); nd = int(sys.argv[2])
 sim = pqb.GeneralizedCliffordsBSimulationStrategy(U, seed=5, ndev=nd)
 sim.simulate(state, shots)
 best = (1e9, None)
-for r in range(3):
+for r in range(int(os.environ.get('SWEEP_REPS', '3'))):
     sim.seed(5)
     t = time.perf_counter(); res = sim.simulate(state, shots); dt = time.perf_counter() - t
     st = pqb.last_stats()
@@ -25,10 +25,13 @@ print(json.dumps({"shots": shots, "ndev": best[1]["ndev"], "call_ms": best[0] * 
 """ % ROOT
 ndevs = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "1").split(",")]
 shot_list = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "125,1000,20000").split(",")]
-settings = [{}]                                   # the library's own choice
-for tail in ("0", "2", "3", "4", "5"):
-    settings.append({"PQB200_LAP_TAIL": tail})
-settings.append({"PQB200_LAP_TAIL": "3", "PQB200_LAP_WAVES": "1"})
+if len(sys.argv) > 3:                             # explicit list of knob settings (JSON)
+    settings = json.loads(sys.argv[3])
+else:
+    settings = [{}]                               # the library's own choice
+    for tail in ("0", "2", "3", "4", "5"):
+        settings.append({"PQB200_LAP_TAIL": tail})
+    settings.append({"PQB200_LAP_TAIL": "3", "PQB200_LAP_WAVES": "1"})
 for shots in shot_list:
     for nd in ndevs:
         for st in settings:
