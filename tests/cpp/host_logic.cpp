@@ -5,6 +5,7 @@
 #include <string>
 
 #include "../../piquassoboost_b200/csrc/plain_host.h"
+#include "../../piquassoboost_b200/csrc/laplace_host.h"
 #include "../../piquassoboost_b200/csrc/repeated_host.h"
 
 using namespace pqb200;
@@ -69,4 +70,9 @@ int hl_rep_plan(const double* a, size_t rows, size_t cols, size_t stride, const 
     misc[6] = pl.low_parity[1];
     return 0;
 }
+
+// launch policy of the B sampler (laplace_host.h): CTAs per shot and photon steps left to the cost-ordered
+// second launch, for `shots` shots of `nmax` photons on a device with `sm_count` SMs
+int hl_lap_cluster_for(size_t shots, int sm_count) { return lap_cluster_for(shots, sm_count); }
+int hl_lap_tail_steps(size_t shots, int nmax, int sm_count) { return lap_tail_steps(shots, nmax, sm_count); }
 }

@@ -192,3 +192,28 @@ def test_rng_replay_header_matches_std_mt19937(tmp_path):
                    check=True, capture_output=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
+
+
+def test_sampler_launch_policy(hl, monkeypatch):
+    """laplace_host.h: clusters only while all their CTAs are resident at once (3 CTAs per SM), a second,
+    cost-ordered launch only when the shots fill the device, never both (the second launch runs one CTA per
+    shot), and the tuning knobs override the choice."""
+    for k in ("PQB200_LAP_CLUSTER", "PQB200_LAP_TAIL"):
+        monkeypatch.delenv(k, raising=False)
+    hl.hl_lap_cluster_for.argtypes = [ctypes.c_size_t, ctypes.c_int]
+    hl.hl_lap_tail_steps.argtypes = [ctypes.c_size_t, ctypes.c_int, ctypes.c_int]
+    sms, slots = 148, 148 * 3
+    for shots in list(range(1, 700)) + [1000, 2664, 2665, 5000, 20000, 10**6]:
+        cs = hl.hl_lap_cluster_for(shots, sms)
+        tail = hl.hl_lap_tail_steps(shots, 20, sms)
+        assert 1 <= cs <= 8
+        assert cs == 1 or cs * shots <= slots            # every CTA of every cluster resident in one wave
+        assert cs > 1 or shots * 2 > slots                # SMs to spare are used
+        assert tail in (0, 4) and not (tail and cs > 1)
+        assert (tail == 4) == (slots <= shots <= 6 * slots)
+    assert hl.hl_lap_cluster_for(125, sms) == 3 and hl.hl_lap_cluster_for(25, sms) == 8
+    assert hl.hl_lap_cluster_for(60, sms) == 4          # 8 CTAs per shot only with SMs to spare
+    assert hl.hl_lap_tail_steps(1000, 8, sms) == 0      # few photons: one launch
+    monkeypatch.setenv("PQB200_LAP_TAIL", "2")
+    monkeypatch.setenv("PQB200_LAP_CLUSTER", "2")
+    assert hl.hl_lap_tail_steps(100, 20, sms) == 2 and hl.hl_lap_cluster_for(1000, sms) == 2
