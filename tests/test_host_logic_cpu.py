@@ -217,3 +217,58 @@ def test_sampler_launch_policy(hl, monkeypatch):
     monkeypatch.setenv("PQB200_LAP_TAIL", "2")
     monkeypatch.setenv("PQB200_LAP_CLUSTER", "2")
     assert hl.hl_lap_tail_steps(100, 20, sms) == 2 and hl.hl_lap_cluster_for(1000, sms) == 2
+
+
+def _laplace_pmf(U, sample, cur):
+    """laplace_sampler_kernel's photon step in numpy (csrc/laplace_sampler.cuh): ONE mixed-radix Gray sweep over
+    the row multiplicities; every term is the vector of column sums with one factor left out (prefix / suffix
+    products), which yields all k sub-permanents of compute_pmf (samplingHelperFunctions.cpp:137-172) at once."""
+    import itertools
+    from math import comb
+    m = len(sample)
+    cols = [j for j in range(m) for _ in range(int(cur[j]))]          # physically repeated columns
+    first = [i == 0 or cols[i] != cols[i - 1] for i in range(len(cols))]
+    N, K = len(cols), int(np.sum(sample))
+    if K == 0:
+        addend = np.ones(N, dtype=complex)
+    else:
+        occ = [i for i in range(m) if sample[i] > 0]
+        amin = min(occ, key=lambda i: (sample[i], i))                   # anchor: first minimum-multiplicity row
+        rows = [(i, int(sample[i]) - (1 if i == amin else 0)) for i in occ]
+        rows = [(i, r) for i, r in rows if r > 0]
+        A0 = U[amin, cols]
+        addend = np.zeros(N, dtype=complex)
+        for ks in itertools.product(*[range(r + 1) for _, r in rows]):
+            s = A0.copy()
+            w = 1.0
+            for (i, r), k in zip(rows, ks):
+                s = s + (r - 2 * k) * U[i, cols]
+                w *= comb(r, k) * (-1) ** k
+            pre = np.concatenate(([1.0 + 0j], np.cumprod(s)[:-1]))
+            suf = np.concatenate((np.cumprod(s[::-1])[::-1][1:], [1.0 + 0j]))
+            addend += w * pre * suf                                     # leave-one-out products of the term
+        addend *= 2.0 ** -(K - 1)
+    amp = np.zeros(m, dtype=complex)
+    for j in range(N):
+        if first[j]:
+            amp += cur[cols[j]] * addend[j] * U[:, cols[j]]
+    p = np.abs(amp) ** 2
+    return p / p.sum()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_laplace_sweep_restatement_matches_oracle_pmf(seed):
+    """The sampler kernel's algorithm (one sweep, leave-one-out products: Clifford & Clifford's Lemma 1 as in
+    piquasso-module/src/permanent_laplace.cpp:43-233) against the oracle's compute_pmf, which evaluates the k
+    repeated sub-permanents one by one as the reference does -- including collisions on both sides."""
+    from oracle import oraclebind
+    rng = np.random.default_rng(seed)
+    m = 5 + seed % 4
+    U = haar_unitary(m, 40 + seed)
+    for _ in range(6):
+        k = int(rng.integers(1, 7))                                    # photons inserted so far
+        cur = np.bincount(rng.integers(0, m, size=k), minlength=m)
+        sample = np.bincount(rng.integers(0, max(2, m // 2), size=k - 1), minlength=m)  # k-1 placed, with collisions
+        want = oraclebind.compute_pmf(U, sample, cur)
+        got = _laplace_pmf(U, sample, cur)
+        assert np.allclose(got, want, rtol=1e-10, atol=1e-14), (sample, cur)
