@@ -272,3 +272,15 @@ def test_laplace_sweep_restatement_matches_oracle_pmf(seed):
         want = oraclebind.compute_pmf(U, sample, cur)
         got = _laplace_pmf(U, sample, cur)
         assert np.allclose(got, want, rtol=1e-10, atol=1e-14), (sample, cur)
+
+
+def test_double_double_primitives_against_float128(tmp_path):
+    """csrc/dd.cuh compiled for the host (tests/cpp/dd_arith.cpp): TwoSum is error-free, dd add / multiply and
+    the complex dd product are accurate to 2^-100 against __float128, a 2e6-term cancelling sum keeps 2^-95 of
+    sum|x| (plain double: 1e-17) -- the accumulation every kernel uses and the arithmetic of pqb200_permanent_dd,
+    which serves the reference's long double / MPFR requests."""
+    exe = str(tmp_path / "dd_arith")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(ROOT, "tests", "cpp", "dd_arith.cpp")],
+                   check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
