@@ -5,6 +5,7 @@
 #include <string>
 
 #include "../../piquassoboost_b200/csrc/plain_host.h"
+#include "../../piquassoboost_b200/csrc/batch_host.h"
 #include "../../piquassoboost_b200/csrc/laplace_host.h"
 #include "../../piquassoboost_b200/csrc/repeated_host.h"
 
@@ -75,4 +76,27 @@ int hl_rep_plan(const double* a, size_t rows, size_t cols, size_t stride, const 
 // second launch, for `shots` shots of `nmax` photons on a device with `sm_count` SMs
 int hl_lap_cluster_for(size_t shots, int sm_count) { return lap_cluster_for(shots, sm_count); }
 int hl_lap_tail_steps(size_t shots, int nmax, int sm_count) { return lap_tail_steps(shots, nmax, sm_count); }
+
+// One job of the batch path (batch_host.h: index lists only).  Returns make_batch_job's code (0 ok / 2 / 3);
+// head = {kind, R, N, q, len, nchunks, transpose}, gidx[R], radix[R-1], pidx[N].
+int hl_batch_job(size_t rows, size_t cols, const int64_t* row_mult, const int64_t* col_mult, long long* head,
+                 int* gidx, int* radix, int* pidx) {
+    BatchJobHost job;
+    memset(&job, 0, sizeof(job));
+    BatchJobKind kind = kJobKernel;
+    std::string err;
+    const int rc = make_batch_job(rows, cols, row_mult, col_mult, job, kind, err);
+    head[0] = (long long)kind;
+    if (rc || kind == kJobTrivialOne || kind == kJobTooBig) return rc;
+    head[1] = job.R;
+    head[2] = job.N;
+    head[3] = job.q;
+    head[4] = job.len;
+    head[5] = job.nchunks;
+    head[6] = job.transpose;
+    for (int i = 0; i < job.R; i++) gidx[i] = job.gidx[i];
+    for (int i = 0; i + 1 < job.R; i++) radix[i] = job.radix[i];
+    for (int i = 0; i < job.N; i++) pidx[i] = job.pidx[i];
+    return 0;
+}
 }

@@ -284,3 +284,67 @@ def test_double_double_primitives_against_float128(tmp_path):
                    check=True, capture_output=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
+
+
+def _batch_job(hl, rm, cm):
+    rm = np.ascontiguousarray(rm, dtype=np.int64)
+    cm = np.ascontiguousarray(cm, dtype=np.int64)
+    head = np.zeros(8, dtype=np.int64)
+    gidx, radix, pidx = (np.zeros(64, dtype=np.int32) for _ in range(3))
+    rc = hl.hl_batch_job(ctypes.c_size_t(len(rm)), ctypes.c_size_t(len(cm)), rm.ctypes.data_as(_lp), cm.ctypes.data_as(_lp),
+                         head.ctypes.data_as(_lp), gidx.ctypes.data_as(_ip), radix.ctypes.data_as(_ip), pidx.ctypes.data_as(_ip))
+    kind, R, N, q, length, nchunks, tr = (int(x) for x in head[:7])
+    return rc, dict(kind=kind, R=R, N=N, q=q, len=length, nchunks=nchunks, transpose=tr,
+                    gidx=gidx[:R].tolist(), radix=radix[:max(R - 1, 0)].tolist(), pidx=pidx[:N].tolist())
+
+
+def test_batch_job_construction_matches_oracle(hl):
+    """batch_host.h builds a job of the many-small-permanents path from the two states alone (index lists: the
+    gather of adaptInterferometer, BatchedPermanentCalculator.cpp:412-451, happens in the kernel prologue).
+    glynn_batch_kernel's sum is emulated from the job in numpy and compared with the oracle's repeated
+    permanent; the Gray side is the one with the smaller space, the digit split covers it exactly."""
+    import itertools
+    from math import comb
+    from oracle import oraclebind
+    rng = np.random.default_rng(11)
+    m = 7
+    U = haar_unitary(m, 77)
+    kinds = set()
+    for case in range(60):
+        photons = int(rng.integers(0, 7))
+        rm = np.bincount(rng.integers(0, m, size=photons), minlength=m)
+        cm = np.bincount(rng.integers(0, 3 if case % 2 else m, size=photons), minlength=m)
+        rc, job = _batch_job(hl, rm, cm)
+        assert rc == 0
+        kinds.add(job["kind"])
+        want = oraclebind.bbfg_repeated(U, cm, rm)      # (matrix, input = columns, output = rows)
+        if job["kind"] == 1:                             # empty permanent
+            assert photons == 0 and want == 1
+            continue
+        assert job["kind"] in (0, 2) and job["N"] == photons
+        el = (lambda g, p: U[p, g]) if job["transpose"] else (lambda g, p: U[g, p])
+        A = np.array([[el(g, p) for p in job["pidx"]] for g in job["gidx"]])
+        if job["kind"] == 2:                             # a single row of multiplicity 1: the product of its entries
+            assert job["R"] == 1 and photons == 1
+            got = np.prod(A[0])
+        else:
+            total = int(np.prod(job["radix"]))
+            assert job["len"] * job["nchunks"] == total and job["len"] == int(np.prod(job["radix"][:job["q"]]))
+            got = 0.0
+            for ks in itertools.product(*[range(r) for r in job["radix"]]):
+                s = A[0].copy()
+                w = 1.0
+                for d, k in enumerate(ks):
+                    r = job["radix"][d] - 1
+                    s = s + (r - 2 * k) * A[d + 1]
+                    w *= comb(r, k) * (-1) ** k
+                got += w * np.prod(s)
+            got *= 2.0 ** -(photons - 1)
+            # the Gray side is the smaller space
+            space = lambda mult: np.prod([v + 1 for v in mult if v > 0]) * min(v for v in mult if v > 0) / (min(v for v in mult if v > 0) + 1)
+            assert (space(cm) < space(rm)) == bool(job["transpose"])
+        assert relerr(got, want) < 1e-12, (rm, cm, job)
+    assert kinds >= {0, 1}
+    # error codes of the reference: unequal photon numbers, negative occupation
+    assert _batch_job(hl, [1, 0, 2], [1, 1, 0])[0] == 3
+    assert _batch_job(hl, [1, -1, 0], [0, 0, 0])[0] == 2
