@@ -284,7 +284,7 @@ def run_b200(args, rank, local_rank, world):
         cpu_equiv, cpu_desc, _ = cpu_reference_rate(n, args.cpu_seconds)
         # the value of THIS run's permanent against the committed golden values: the reference's own long
         # double where one exists (n <= 38, tools/ref_big.py), else the double-double evaluation (itself
-        # pinned to the reference's long double up to n=38; tests/golden/plain_dd_reference.json)
+        # pinned to the reference's long double up to n=40; tests/golden/plain_dd_reference.json)
         accuracy = None
         try:
             gold = json.load(open(os.path.join(ROOT, "tests", "golden", "plain_dd_reference.json")))["cases"]
